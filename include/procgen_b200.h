@@ -1,0 +1,174 @@
+/* procgen_b200 — C ABI of the B200 vectorised Procgen backend (libprocgen_b200.so).
+ *
+ * Part 1 is the libenv interface that the reference's libenv.so exports and that gym3's
+ * `CEnv` binds through cffi (reference: procgen/src/vecgame.cpp:42-99 for the seven libenv_*
+ * entry points, :437-457 for get_state/set_state, declared to cffi at procgen/env.py:132-135).
+ * The struct layouts restate gym3==0.3.3 `gym3/libenv.h` (pinned by environment.yml:12), which is
+ * not vendored in the reference tree; they are reconstructed from their uses in vecgame.cpp:212-282
+ * (libenv_tensortype), vecoptions.cpp:4-54 (libenv_option[s]) and vecgame.cpp:30-40,74-83
+ * (libenv_buffers: bufs[space_idx * num_envs + env_idx]).
+ *
+ * Part 2 is the device-resident extension: the same environment, but observations, rewards,
+ * firsts, infos and actions stay in HBM and are exposed as raw device pointers (plain pointers
+ * and sizes, no framework types) so a caller can wrap them as tensors without a host round trip.
+ */
+#ifndef PROCGEN_B200_H
+#define PROCGEN_B200_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define LIBENV_API __declspec(dllexport)
+#else
+#define LIBENV_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------ Part 1: libenv */
+
+#define LIBENV_VERSION 1
+#define LIBENV_MAX_NAME_LEN 128
+#define LIBENV_MAX_NDIM 16
+
+enum libenv_dtype {
+    LIBENV_DTYPE_UNUSED = 0,
+    LIBENV_DTYPE_UINT8 = 1,
+    LIBENV_DTYPE_INT32 = 2,
+    LIBENV_DTYPE_FLOAT32 = 3,
+};
+
+enum libenv_scalar_type {
+    LIBENV_SCALAR_TYPE_UNUSED = 0,
+    LIBENV_SCALAR_TYPE_REAL = 1,
+    LIBENV_SCALAR_TYPE_DISCRETE = 2,
+};
+
+enum libenv_space_name {
+    LIBENV_SPACE_UNUSED = 0,
+    LIBENV_SPACE_OBSERVATION = 1,
+    LIBENV_SPACE_ACTION = 2,
+    LIBENV_SPACE_INFO = 3,
+};
+
+union libenv_value {
+    uint8_t uint8;
+    int32_t int32;
+    float float32;
+};
+
+struct libenv_tensortype {
+    char name[LIBENV_MAX_NAME_LEN];
+    enum libenv_scalar_type scalar_type;
+    enum libenv_dtype dtype;
+    int shape[LIBENV_MAX_NDIM];
+    int ndim;
+    union libenv_value low;
+    union libenv_value high;
+};
+
+struct libenv_option {
+    char name[LIBENV_MAX_NAME_LEN];
+    enum libenv_dtype dtype;
+    int count;
+    void *data;
+};
+
+struct libenv_options {
+    struct libenv_option *items;
+    int count;
+};
+
+struct libenv_buffers {
+    void **ob;      /* [n_ob_spaces * num_envs], index space_idx * num_envs + env_idx */
+    float *rew;     /* [num_envs] */
+    uint8_t *first; /* [num_envs] */
+    void **info;    /* [n_info_spaces * num_envs] */
+    void **ac;      /* [n_ac_spaces * num_envs] */
+};
+
+typedef void libenv_env;
+
+/* vecgame.cpp:43-45 */
+LIBENV_API int libenv_version(void);
+
+/* vecgame.cpp:47-50. Options consumed: every option of VecGame::VecGame (vecgame.cpp:183-190:
+ * env_name, num_levels, start_level, num_actions, rand_seed, num_threads, resource_root,
+ * render_human) and of Game::parse_options (game.cpp:42-75).  Unknown options are fatal
+ * (vecoptions.cpp:34-38).  num_threads is accepted and ignored: stepping is one asynchronous
+ * kernel launch per act().  resource_root names the directory holding assets.pack (or the pack
+ * file itself).  Extra, optional int32 options understood by this backend only:
+ *   cuda_device        device ordinal (default: current device)
+ *   env_index_offset   global index of env 0 when one logical VecGame of `env_index_total` envs
+ *   env_index_total    is sharded over several handles/GPUs; the per-env seed chain
+ *                      (vecgame.cpp:301-314) and game_n are replayed for the global indices
+ *   snap_target_rect   uint8 bool, default 1: Qt>=6 integer snapping of un-rotated image targets */
+LIBENV_API libenv_env *libenv_make(int num_envs, const struct libenv_options options);
+
+/* vecgame.cpp:52-72; `types` may be NULL to query the count. */
+LIBENV_API int libenv_get_tensortypes(libenv_env *handle, enum libenv_space_name name, struct libenv_tensortype *types);
+
+/* vecgame.cpp:74-83 -> VecGame::set_buffers (:333-361): stores the caller-owned HOST pointers and
+ * performs the initial reset + observe of every env. */
+LIBENV_API void libenv_set_buffers(libenv_env *handle, struct libenv_buffers *bufs);
+
+/* vecgame.cpp:85-88 -> VecGame::observe (:363-376): waits for the step in flight and fills the
+ * host buffers given to libenv_set_buffers. */
+LIBENV_API void libenv_observe(libenv_env *handle);
+
+/* vecgame.cpp:90-93 -> VecGame::act (:378-401): copies the actions out of the host buffers
+ * (they are only valid during this call) and starts the step asynchronously. */
+LIBENV_API void libenv_act(libenv_env *handle);
+
+/* vecgame.cpp:95-98 */
+LIBENV_API void libenv_close(libenv_env *handle);
+
+/* ------------------------------------------------------------------ Part 2: device-resident */
+
+struct pgb200_device_buffers {
+    uint8_t *rgb;                  /* [num_envs][64][64][3] uint8, device */
+    float *rew;                    /* [num_envs] */
+    uint8_t *first;                /* [num_envs] */
+    int32_t *prev_level_seed;      /* [num_envs] info */
+    uint8_t *prev_level_complete;  /* [num_envs] info */
+    int32_t *level_seed;           /* [num_envs] info */
+    int32_t *action;               /* [num_envs], written by the caller before pgb200_act_device */
+    int32_t num_envs;
+    int32_t device;                /* CUDA device ordinal, -1 for the CPU debug build */
+    void *stream;                  /* cudaStream_t all work of this handle is ordered on */
+};
+
+/* Returns 0 on success. The first call performs the initial reset + render (the work
+ * libenv_set_buffers does in host mode). Pointers stay valid until libenv_close. */
+LIBENV_API int pgb200_get_device_buffers(libenv_env *handle, struct pgb200_device_buffers *out);
+
+/* Re-home all subsequent work of this handle onto the caller's stream (a cudaStream_t, e.g. the
+ * framework's current stream) so launches are ordered with the caller's own kernels and copies
+ * without events. The handle's previous work is drained first. NULL restores the private stream. */
+LIBENV_API void pgb200_set_stream(libenv_env *handle, void *stream);
+
+/* Steps every env with the actions currently in the device action buffer. Asynchronous: enqueues
+ * on the handle's stream and returns. */
+LIBENV_API void pgb200_act_device(libenv_env *handle);
+
+/* Blocks until all enqueued work of this handle is complete (VecGame::wait_for_stepping_threads). */
+LIBENV_API void pgb200_sync(libenv_env *handle);
+
+/* Per-env sticky error bits (0 = healthy): where the reference would fassert/exit, the device code
+ * latches a bit instead. Copies num_envs words to `host_out`; returns the OR of all of them. */
+LIBENV_API uint32_t pgb200_get_errors(libenv_env *handle, uint32_t *host_out);
+
+/* Number of CUDA kernels this handle has launched so far (bench accounting). */
+LIBENV_API int64_t pgb200_kernel_launches(libenv_env *handle);
+
+/* 1 if this library was built for the GPU (the product), 0 for the CPU debug harness in tests/. */
+LIBENV_API int pgb200_is_device_build(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PROCGEN_B200_H */

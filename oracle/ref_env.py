@@ -78,7 +78,8 @@ class RefVecEnv:
     def __init__(self, num, env_name, distribution_mode="hard", num_levels=0, start_level=0, rand_seed=0,
                  num_threads=0, center_agent=True, use_backgrounds=True, use_monochrome_assets=False,
                  restrict_themes=False, use_generated_assets=False, paint_vel_info=False,
-                 use_sequential_levels=False, debug_mode=0, lib_path=None, pack_path=None):
+                 use_sequential_levels=False, debug_mode=0, lib_path=None, pack_path=None, resource_root=None,
+                 extra_options=None):
         lib_path = lib_path or REF_LIB
         if not os.path.exists(lib_path):
             raise FileNotFoundError(f"{lib_path} missing — run python oracle/build_ref.py in the build container")
@@ -91,21 +92,23 @@ class RefVecEnv:
         for f in (L.libenv_observe, L.libenv_act, L.libenv_close):
             f.argtypes = [C.c_void_p]
             f.restype = None
-        L.get_state.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
-        L.get_state.restype = C.c_int
-        L.set_state.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
-        L.set_state.restype = None
+        if hasattr(L, "get_state"):
+            L.get_state.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+            L.get_state.restype = C.c_int
+            L.set_state.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+            L.set_state.restype = None
         self.num = num
         self._keep = []
         opts = dict(
             env_name=env_name, num_levels=num_levels, start_level=start_level, num_actions=15,
             use_sequential_levels=bool(use_sequential_levels), debug_mode=debug_mode, rand_seed=rand_seed,
             num_threads=num_threads, render_human=False,
-            resource_root=(pack_path or default_pack()) + ":",
+            resource_root=resource_root if resource_root is not None else (pack_path or default_pack()) + ":",
             center_agent=bool(center_agent), use_generated_assets=bool(use_generated_assets),
             use_monochrome_assets=bool(use_monochrome_assets), restrict_themes=bool(restrict_themes),
             use_backgrounds=bool(use_backgrounds), paint_vel_info=bool(paint_vel_info),
             distribution_mode=DISTRIBUTION_MODE[distribution_mode])
+        opts.update(extra_options or {})
         self.h = L.libenv_make(num, make_options(self._keep, **opts))
         n_info = L.libenv_get_tensortypes(self.h, SPACE_INFO, None)
         info_types = (TensorType * n_info)()

@@ -1,0 +1,59 @@
+// Which image files each game binds to each object type, and which background group it uses.
+// Data restated from every games/<name>.cpp `asset_for_type` / `load_background_images`
+// (file:line cited per game). Host only.
+#pragma once
+#include "pg_assets_host.h"
+
+namespace pg {
+namespace host {
+
+inline GameAssetNames game_asset_names(int game_id) {
+    GameAssetNames g;
+    auto &T = g.by_type;
+    switch (game_id) {
+    case GAME_COINRUN: {  // coinrun.cpp:59-121
+        g.bg_group = "platform_backgrounds";
+        const char *colors[5] = {"Beige", "Blue", "Green", "Pink", "Yellow"};
+        const char *poses[4] = {"stand", "jump", "walk1", "walk2"};
+        const int pose_type[4] = {0 /*PLAYER*/, 9 /*PLAYER_JUMP*/, 12 /*PLAYER_RIGHT1*/, 13 /*PLAYER_RIGHT2*/};
+        for (int p = 0; p < 4; p++)
+            for (auto col : colors)
+                T[pose_type[p]].push_back(std::string("kenney/Players/128x256/") + col + "/alien" + col + "_" + poses[p] + ".png");
+        const char *enemies[9] = {"slimeBlock", "slimePurple", "slimeBlue", "slimeGreen", "mouse", "snail", "ladybug", "wormGreen", "wormPink"};
+        for (auto e : enemies) {
+            T[6].push_back(std::string("kenney/Enemies/") + e + ".png");       // ENEMY1
+            T[7].push_back(std::string("kenney/Enemies/") + e + "_move.png");  // ENEMY2
+        }
+        T[1] = {"kenney/Items/coinGold.png"};  // GOAL
+        const char *grounds[6] = {"Dirt", "Grass", "Planet", "Sand", "Snow", "Stone"};
+        for (auto gr : grounds) {
+            T[16].push_back(std::string("kenney/Ground/") + gr + "/" + lower(gr) + "Mid.png");     // WALL_TOP
+            T[15].push_back(std::string("kenney/Ground/") + gr + "/" + lower(gr) + "Center.png");  // WALL_MID
+        }
+        T[18] = {"kenney/Tiles/lavaTop_low.png"};  // LAVA_TOP
+        T[17] = {"kenney/Tiles/lava.png"};         // LAVA_MID
+        T[2] = {"kenney/Enemies/sawHalf.png"};
+        T[3] = {"kenney/Enemies/sawHalf_move.png"};
+        T[20] = {"kenney/Tiles/boxCrate.png", "kenney/Tiles/boxCrate_double.png", "kenney/Tiles/boxCrate_single.png",
+                 "kenney/Tiles/boxCrate_warning.png"};
+        break;
+    }
+    case GAME_BIGFISH:  // bigfish.cpp:31-43
+        g.bg_group = "water_backgrounds";
+        T[0] = {"misc_assets/fishTile_072.png"};
+        T[2] = {"misc_assets/fishTile_074.png", "misc_assets/fishTile_078.png", "misc_assets/fishTile_080.png"};
+        break;
+    case GAME_MAZE:  // maze.cpp:26-38
+        g.bg_group = "topdown_backgrounds";
+        T[51] = {"kenney/Ground/Sand/sandCenter.png"};
+        T[2] = {"misc_assets/cheese.png"};
+        T[0] = {"kenney/Enemies/mouse_move.png"};
+        break;
+    default:
+        throw std::runtime_error("procgen_b200: game id " + std::to_string(game_id) + " has no asset table yet");
+    }
+    return g;
+}
+
+}  // namespace host
+}  // namespace pg

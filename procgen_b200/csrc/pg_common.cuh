@@ -1,0 +1,133 @@
+// procgen_b200 — shared definitions for the device engine.
+//
+// Everything marked PG_HD compiles for sm_100a (product) and, for the CPU debugging harness under
+// tests/hostsim only, as plain host C++ (g++ -x c++).  The host build exists so the bit-exact
+// float/integer semantics can be diffed against the oracle without a GPU in the loop; it is never
+// linked into the product library and the product has no CPU path.
+//
+// Float semantics (SURVEY §7 hard part 1): the reference is C++ that mixes float and double
+// freely and whose published wheels are built without FMA (CMakeLists.txt:30).  Device code is
+// compiled with -fmad=false and written with the same operand types as the reference expression
+// it mirrors; libm calls that the reference resolves to the C `double` overloads (unqualified
+// sqrt/floor/ceil/fabs on floats — checked in the oracle's disassembly) go through the pg_d*
+// helpers below so nvcc cannot pick the float overloads.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PG_HD __host__ __device__ __forceinline__
+#define PG_HD_NOINLINE __host__ __device__ __noinline__
+#define PG_D __device__ __forceinline__
+#else
+#define PG_HD inline
+#define PG_HD_NOINLINE
+#define PG_D inline
+#endif
+
+namespace pg {
+
+// ---- observation contract (game.h:24-27): constants forever
+constexpr int RES_W = 64;
+constexpr int RES_H = 64;
+
+// ---- object ids (object-ids.h:9-26)
+constexpr int INVALID_OBJ = -1;
+constexpr int INVALID_IDX = -2;
+constexpr int PLAYER = 0;
+constexpr int SPACE = 100;
+constexpr int WALL_OBJ = 51;
+constexpr int EXIT_OBJ = 52;
+constexpr int AGENT_OBJ = 53;
+constexpr int EXPLOSION = 54;
+constexpr int EXPLOSION2 = 55;
+constexpr int EXPLOSION3 = 56;
+constexpr int EXPLOSION4 = 57;
+constexpr int EXPLOSION5 = 58;
+constexpr int TRAIL = 59;
+constexpr int DOOR_OBJ = 200;
+constexpr int KEY_OBJ = 300;
+
+// ---- engine constants (basic-abstract-game.cpp:6-20, cpp-utils.h:12)
+constexpr float PI_F = 3.14159265358979323846264338327950288f;
+constexpr float MAXVTHETA = 15 * PI_F / 180;
+constexpr float MIXRATEROT = 0.5f;
+constexpr float POS_EPS = -0.001f;
+constexpr float RENDER_EPS = 0.02f;
+constexpr int USE_ASSET_THRESHOLD = 100;
+constexpr int MAX_ASSETS = USE_ASSET_THRESHOLD;
+constexpr int MAX_IMAGE_THEMES = 10;
+
+// ---- distribution modes (game.h:32-37)
+constexpr int EasyMode = 0;
+constexpr int HardMode = 1;
+constexpr int ExtremeMode = 2;
+constexpr int MemoryMode = 10;
+
+// ---- game ids (order = alphabetical, the registry is a name->factory map, game-registry.h)
+enum GameId : int {
+    GAME_BIGFISH = 0,
+    GAME_BOSSFIGHT,
+    GAME_CAVEFLYER,
+    GAME_CHASER,
+    GAME_CLIMBER,
+    GAME_COINRUN,
+    GAME_DODGEBALL,
+    GAME_FRUITBOT,
+    GAME_HEIST,
+    GAME_JUMPER,
+    GAME_LEAPER,
+    GAME_MAZE,
+    GAME_MINER,
+    GAME_NINJA,
+    GAME_PLUNDER,
+    GAME_STARPILOT,
+    NUM_GAMES
+};
+
+// ---- double-precision libm shims (the reference calls the C double overloads)
+PG_HD double pg_dsqrt(double x) { return sqrt(x); }
+PG_HD double pg_dfloor(double x) { return floor(x); }
+PG_HD double pg_dceil(double x) { return ceil(x); }
+PG_HD double pg_dfabs(double x) { return fabs(x); }
+
+// cpp-utils.h:43-45 — returns double on purpose
+PG_HD double pg_sign(double x) { return x > 0 ? +1 : (x == 0 ? 0 : -1); }
+
+// cpp-utils.h:47-53
+PG_HD float pg_clip_abs(float x, float y) {
+    if (x > y)
+        return y;
+    if (x < -y)
+        return -y;
+    return x;
+}
+
+// Qt's qRound(double) (qglobal.h) — round half up, used by every raster rule
+PG_HD int pg_qround(double d) {
+    return d >= 0.0 ? int(d + 0.5) : int(d - double(int(d - 1)) + 0.5) + int(d - 1);
+}
+
+// Qt's BYTE_MUL on a packed 0xAARRGGBB word (qdrawhelper_p.h)
+PG_HD uint32_t pg_byte_mul(uint32_t x, uint32_t a) {
+    uint32_t t = (x & 0xff00ffu) * a;
+    t = (t + ((t >> 8) & 0xff00ffu) + 0x800080u) >> 8;
+    t &= 0xff00ffu;
+    x = ((x >> 8) & 0xff00ffu) * a;
+    x = (x + ((x >> 8) & 0xff00ffu) + 0x800080u);
+    x &= 0xff00ff00u;
+    return x | t;
+}
+
+// error bits latched per env (the reference would fassert/exit; we must not kill the GPU)
+enum ErrBits : uint32_t {
+    ERR_ENTITY_OVERFLOW = 1u << 0,
+    ERR_GRID_OOB = 1u << 1,
+    ERR_BLIT_OVERFLOW = 1u << 2,
+    ERR_SCRATCH_OVERFLOW = 1u << 3,
+    ERR_FASSERT = 1u << 4,
+    ERR_UNSUPPORTED = 1u << 5,
+};
+
+}  // namespace pg

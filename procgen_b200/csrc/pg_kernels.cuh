@@ -1,0 +1,129 @@
+// Per-env work items (logic phase, render phases) and the launch parameter block. The CUDA
+// kernels in pg_runtime.cu are thin wrappers that map one CTA to one env and put barriers between
+// the phases; the CPU debug harness runs the very same phase functions in plain loops.
+#pragma once
+#include "pg_raster.cuh"
+
+namespace pg {
+
+struct KParams {
+    // state (HBM)
+    EnvHdr *hdr;
+    Entity *ents;
+    int16_t *grid;
+    MT19937 *rng;
+    MT19937 *lvl_rng;
+    int32_t *scratch;
+    const GameAssets *assets;   // table of the game this launch handles
+    const uint32_t *atlas;
+    // libenv-visible buffers (vecgame.cpp:212-268), one slot per env
+    const int32_t *action;
+    uint8_t *rgb;               // [N][64][64][3]
+    float *rew;
+    uint8_t *first;
+    int32_t *info_prev_level_seed;
+    uint8_t *info_prev_level_complete;
+    int32_t *info_level_seed;
+    const uint32_t *lvl_seeds;  // per-env seed for level_seed_rand_gen (vecgame.cpp:301-314)
+    // strides (elements)
+    int32_t ent_stride;         // ent_cap + 1 (ghost slot)
+    int32_t grid_stride;
+    int32_t scratch_stride;
+    // which envs this launch covers: env = env_first + i * env_step, i in [0, env_count)
+    int32_t env_first, env_step, env_count;
+    // construction-time options (game.cpp:42-75, vecgame.cpp:284-293)
+    Options options;
+    int32_t level_seed_low, level_seed_high;
+    int32_t game_id;
+    int32_t snap;
+    int32_t env_global_offset;  // game_n = env_global_offset + env
+};
+
+PG_HD Ctx make_ctx(const KParams &p, int env) {
+    Ctx c;
+    c.h = p.hdr + env;
+    c.ents = p.ents + (size_t)env * p.ent_stride;
+    c.grid = p.grid + (size_t)env * p.grid_stride;
+    c.rng = p.rng + env;
+    c.lvl_rng = p.lvl_rng + env;
+    c.assets = p.assets;
+    c.scratch = p.scratch + (size_t)env * p.scratch_stride;
+    c.ent_cap = p.ent_stride - 1;
+    c.grid_cap = p.grid_stride;
+    c.scratch_cap = p.scratch_stride;
+    return c;
+}
+
+// Game::observe's scalar stores (game.cpp:160-164)
+PG_HD void write_step_outputs(const KParams &p, int env, const EnvHdr &h) {
+    p.rew[env] = h.reward;
+    p.first[env] = (uint8_t)(h.done != 0);
+    p.info_prev_level_seed[env] = h.prev_level_seed;
+    p.info_prev_level_complete[env] = (uint8_t)(h.level_complete != 0);
+    p.info_level_seed[env] = h.current_level_seed;
+}
+
+// Construction + first reset (VecGame ctor per-env part vecgame.cpp:309-330, then
+// set_buffers -> reset(); observe(), vecgame.cpp:349-353). One thread.
+template <class G, class Frame>
+PG_HD void env_init_logic(const KParams &p, int env, Frame &f) {
+    Ctx c = make_ctx(p, env);
+    G::init_constants(c);
+    EnvHdr &h = *c.h;
+    h.options = p.options;
+    h.game_id = p.game_id;
+    h.game_n = p.env_global_offset + env;
+    h.level_seed_low = p.level_seed_low;
+    h.level_seed_high = p.level_seed_high;
+    mt_seed(*c.lvl_rng, p.lvl_seeds[env]);
+    c.rng->seeded = 0;
+    Engine<G>::reset(c);
+    h.initial_reset_complete = 1;
+    Raster<G, Frame>::frame_setup(c, f, p.snap != 0);
+    write_step_outputs(p, env, h);
+}
+
+// Game::step (game.cpp:120-155) up to, not including, the pixel work. One thread.
+template <class G, class Frame>
+PG_HD void env_step_logic(const KParams &p, int env, Frame &f) {
+    Ctx c = make_ctx(p, env);
+    c.h->action = p.action[env];  // vecgame.cpp:388
+    Engine<G>::step(c);
+    Raster<G, Frame>::frame_setup(c, f, p.snap != 0);
+    write_step_outputs(p, env, *c.h);
+}
+
+template <class G, class Frame>
+PG_HD void env_render_build(const KParams &p, int env, Frame &f, int tid, int nthreads) {
+    Ctx c = make_ctx(p, env);
+    Raster<G, Frame>::frame_build(c, f, tid, nthreads);
+}
+
+// Shade 4 horizontally adjacent pixels and store them as 12 packed RGB bytes (3 aligned words):
+// bgr32_to_rgb888 (game.cpp:8-23) fused into the shader.
+template <class G, class Frame>
+PG_HD void env_render_quad(const KParams &p, int env, const Frame &f, int quad) {
+    const int py = quad >> 4;
+    const int px0 = (quad & 15) << 2;
+    uint32_t c0 = Raster<G, Frame>::shade_pixel(f, px0 + 0, py, p.atlas);
+    uint32_t c1 = Raster<G, Frame>::shade_pixel(f, px0 + 1, py, p.atlas);
+    uint32_t c2 = Raster<G, Frame>::shade_pixel(f, px0 + 2, py, p.atlas);
+    uint32_t c3 = Raster<G, Frame>::shade_pixel(f, px0 + 3, py, p.atlas);
+    // 0xAARRGGBB -> bytes R,G,B
+    uint32_t r0 = (c0 >> 16) & 0xff, g0 = (c0 >> 8) & 0xff, b0 = c0 & 0xff;
+    uint32_t r1 = (c1 >> 16) & 0xff, g1 = (c1 >> 8) & 0xff, b1 = c1 & 0xff;
+    uint32_t r2 = (c2 >> 16) & 0xff, g2 = (c2 >> 8) & 0xff, b2 = c2 & 0xff;
+    uint32_t r3 = (c3 >> 16) & 0xff, g3 = (c3 >> 8) & 0xff, b3 = c3 & 0xff;
+    uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3)) + quad * 3;
+    out[0] = r0 | (g0 << 8) | (b0 << 16) | (r1 << 24);
+    out[1] = g1 | (b1 << 8) | (r2 << 16) | (g2 << 24);
+    out[2] = b2 | (r3 << 8) | (g3 << 16) | (b3 << 24);
+}
+
+// Frame sizing per game: visible window (cells per side) and entity capacity.
+template <class G>
+struct FrameFor {
+    using type = FrameT<G::MAX_VIEW_CELLS, G::ENT_CAP>;
+};
+
+}  // namespace pg

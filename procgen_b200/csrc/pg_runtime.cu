@@ -1,0 +1,808 @@
+// libprocgen_b200.so — host runtime + CUDA kernels + the C ABI of include/procgen_b200.h.
+//
+// Replaces the reference's vector runtime (vecgame.cpp: N Game objects + worker-thread pool behind
+// one mutex and two condvars) with: all env state resident in HBM, one CTA per env, one
+// asynchronous kernel launch per act() on a private stream, and observe() = stream wait.
+//
+// Build modes: nvcc (product, sm_100a).  With -DPG_HOSTSIM the same file builds with g++ into the
+// CPU debug harness used ONLY by tests/ (every kernel becomes a plain loop); that build reports
+// pgb200_is_device_build() == 0 and the Python package refuses to load it.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/procgen_b200.h"
+#include "pg_asset_tables.h"
+#include "pg_kernels.cuh"
+#include "games/coinrun.cuh"
+
+#ifndef PG_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+
+using namespace pg;
+
+// ================================================================= errors (cpp-utils.cpp:8-20)
+static void pg_fatal(const char *fmt, ...) {
+    fprintf(stderr, "fatal: ");
+    va_list args;
+    va_start(args, fmt);
+    vfprintf(stderr, fmt, args);
+    va_end(args);
+    exit(EXIT_FAILURE);
+}
+#define pg_fassert(cond)                                                                  \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            fprintf(stderr, "fassert failed '%s' at %s:%d\n", #cond, __FILE__, __LINE__); \
+            exit(EXIT_FAILURE);                                                           \
+        }                                                                                 \
+    } while (0)
+
+#ifndef PG_HOSTSIM
+#define CUDA_CHECK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            pg_fatal("CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
+    } while (0)
+#endif
+
+// ================================================================= option parsing (vecoptions.cpp)
+namespace {
+
+struct OptParser {
+    std::vector<libenv_option> opts;
+    explicit OptParser(const libenv_options &o) : opts(o.items, o.items + o.count) {}
+    bool find(const std::string &name, libenv_dtype dtype, libenv_option *out) {
+        for (size_t i = 0; i < opts.size(); i++) {
+            if (name == std::string(opts[i].name)) {
+                if (opts[i].dtype != dtype)
+                    pg_fatal("invalid dtype for option %s\n", name.c_str());
+                *out = opts[i];
+                opts.erase(opts.begin() + i);
+                return true;
+            }
+        }
+        return false;
+    }
+    void consume_string(const std::string &name, std::string *v) {
+        libenv_option o;
+        if (find(name, LIBENV_DTYPE_UINT8, &o))
+            *v = std::string((char *)o.data, o.count);
+    }
+    void consume_int(const std::string &name, int32_t *v) {
+        libenv_option o;
+        if (find(name, LIBENV_DTYPE_INT32, &o))
+            *v = *(int32_t *)o.data;
+    }
+    void consume_bool(const std::string &name, bool *v) {
+        libenv_option o;
+        if (find(name, LIBENV_DTYPE_UINT8, &o)) {
+            uint8_t b = *(uint8_t *)o.data;
+            pg_fassert(b == 0 || b == 1);
+            *v = (bool)b;
+        }
+    }
+    void ensure_empty() {
+        if (!opts.empty())
+            pg_fatal("unused options found, first unused option: %s\n", opts[0].name);
+    }
+};
+
+std::vector<std::string> split(std::string s, const std::string &delim) {
+    std::vector<std::string> out;
+    size_t pos;
+    while ((pos = s.find(delim)) != std::string::npos) {
+        out.push_back(s.substr(0, pos));
+        s.erase(0, pos + delim.length());
+    }
+    out.push_back(s);
+    return out;
+}
+
+// ================================================================= kernels
+constexpr int kThreads = 128;
+constexpr int kQuads = RES_W * RES_H / 4;
+
+#ifndef PG_HOSTSIM
+template <class G, bool INIT>
+__global__ void __launch_bounds__(kThreads) env_kernel(KParams p) {
+    using Frame = typename FrameFor<G>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Frame &f = *reinterpret_cast<Frame *>(smem_raw);
+    const int env = p.env_first + (int)blockIdx.x * p.env_step;
+    if (threadIdx.x == 0) {
+        if (INIT)
+            env_init_logic<G, Frame>(p, env, f);
+        else
+            env_step_logic<G, Frame>(p, env, f);
+    }
+    __syncthreads();
+    env_render_build<G, Frame>(p, env, f, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    for (int quad = (int)threadIdx.x; quad < kQuads; quad += (int)blockDim.x)
+        env_render_quad<G, Frame>(p, env, f, quad);
+}
+#endif
+
+struct LaunchCtx {
+#ifndef PG_HOSTSIM
+    cudaStream_t stream;
+#endif
+    int64_t *launch_counter;
+};
+
+template <class G, bool INIT>
+void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
+    using Frame = typename FrameFor<G>::type;
+    if (p.env_count <= 0)
+        return;
+#ifndef PG_HOSTSIM
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(env_kernel<G, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Frame)));
+        attr_set = true;
+    }
+    env_kernel<G, INIT><<<p.env_count, kThreads, sizeof(Frame), lc.stream>>>(p);
+    CUDA_CHECK(cudaGetLastError());
+#else
+    static thread_local Frame *f = new Frame;
+    for (int b = 0; b < p.env_count; b++) {
+        int env = p.env_first + b * p.env_step;
+        if (INIT)
+            env_init_logic<G, Frame>(p, env, *f);
+        else
+            env_step_logic<G, Frame>(p, env, *f);
+        env_render_build<G, Frame>(p, env, *f, 0, 1);
+        for (int quad = 0; quad < kQuads; quad++) env_render_quad<G, Frame>(p, env, *f, quad);
+    }
+#endif
+    (*lc.launch_counter)++;
+}
+
+struct GameVTable {
+    const char *name;
+    int id;
+    int ent_cap, grid_cap, scratch_words;
+    void (*init)(const KParams &, const LaunchCtx &);
+    void (*step)(const KParams &, const LaunchCtx &);
+};
+
+template <class G>
+GameVTable make_vtable(int id) {
+    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, &launch_env_kernel<G, true>, &launch_env_kernel<G, false>};
+}
+
+const GameVTable *find_game(const std::string &name) {
+    static const GameVTable table[] = {
+        make_vtable<CoinRun>(GAME_COINRUN),
+    };
+    for (const auto &g : table)
+        if (name == g.name)
+            return &g;
+    return nullptr;
+}
+
+// ================================================================= memory helpers
+template <class T>
+T *dev_alloc(size_t n) {
+    T *ptr = nullptr;
+    if (n == 0)
+        n = 1;
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMalloc((void **)&ptr, n * sizeof(T)));
+    CUDA_CHECK(cudaMemset(ptr, 0, n * sizeof(T)));
+#else
+    ptr = (T *)calloc(n, sizeof(T));
+#endif
+    return ptr;
+}
+void dev_free(void *ptr) {
+#ifndef PG_HOSTSIM
+    if (ptr)
+        cudaFree(ptr);
+#else
+    free(ptr);
+#endif
+}
+void copy_to_dev(void *dst, const void *src, size_t bytes) {
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
+
+// ================================================================= VecEnv (VecGame, vecgame.h)
+struct VecEnv {
+    int num_envs = 0;
+    int device = -1;
+    std::vector<const GameVTable *> games;  // joint games, env n <-> games[n % size] (vecgame.cpp:310)
+    std::vector<libenv_tensortype> observation_types, action_types, info_types;
+    int num_actions = -1;
+
+    KParams base{};                  // common launch parameters
+    std::vector<GameAssets *> d_assets;  // per joint game
+    uint32_t *d_atlas = nullptr;
+    uint32_t *d_lvl_seeds = nullptr;
+    int32_t *d_action = nullptr;
+    bool initial_reset_done = false;
+    int64_t launches = 0;
+
+#ifndef PG_HOSTSIM
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+#endif
+    // host-buffer (libenv) mode
+    bool have_host_bufs = false;
+    bool ob_direct = false;      // caller's obs block is contiguous and page-locked: DMA straight into it
+    bool ob_registered = false;
+    std::vector<void *> h_ob, h_ac;
+    std::vector<std::vector<void *>> h_info;  // [space][env]
+    float *h_rew = nullptr;
+    uint8_t *h_first = nullptr;
+    // pinned staging
+    uint8_t *st_rgb = nullptr;
+    int32_t *st_action = nullptr;
+    float *st_rew = nullptr;
+    uint8_t *st_first = nullptr;
+    int32_t *st_prev_seed = nullptr;
+    uint8_t *st_prev_complete = nullptr;
+    int32_t *st_seed = nullptr;
+
+    LaunchCtx lctx() {
+        LaunchCtx lc;
+#ifndef PG_HOSTSIM
+        lc.stream = stream;
+#endif
+        lc.launch_counter = &launches;
+        return lc;
+    }
+
+    void launch(bool init) {
+        const int G = (int)games.size();
+        for (int g = 0; g < G; g++) {
+            KParams p = base;
+            p.assets = d_assets[g];
+            p.game_id = games[g]->id;
+            p.env_first = g;
+            p.env_step = G;
+            p.env_count = num_envs / G;
+            if (init)
+                games[g]->init(p, lctx());
+            else
+                games[g]->step(p, lctx());
+        }
+    }
+
+    void ensure_initial_reset() {
+        if (initial_reset_done)
+            return;
+        launch(true);
+        initial_reset_done = true;
+    }
+
+    void sync() {
+#ifndef PG_HOSTSIM
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+#endif
+    }
+
+    void set_device() {
+#ifndef PG_HOSTSIM
+        CUDA_CHECK(cudaSetDevice(device));
+#endif
+    }
+};
+
+std::string default_pack_path() {
+    // <dir of this .so>/data/assets.pack, overridable with PROCGEN_B200_ASSET_PACK
+    const char *e = getenv("PROCGEN_B200_ASSET_PACK");
+    if (e && e[0])
+        return e;
+    Dl_info info;
+    if (dladdr((void *)&libenv_version, &info) && info.dli_fname) {
+        std::string so(info.dli_fname);
+        size_t slash = so.rfind('/');
+        std::string dir = slash == std::string::npos ? "." : so.substr(0, slash);
+        return dir + "/data/assets.pack";
+    }
+    return "assets.pack";
+}
+
+void fill_tensortypes(VecEnv *v) {
+    // vecgame.cpp:212-268
+    libenv_tensortype s;
+    memset(&s, 0, sizeof(s));
+    strcpy(s.name, "rgb");
+    s.scalar_type = LIBENV_SCALAR_TYPE_DISCRETE;
+    s.dtype = LIBENV_DTYPE_UINT8;
+    s.shape[0] = RES_W;
+    s.shape[1] = RES_H;
+    s.shape[2] = 3;
+    s.ndim = 3;
+    s.low.uint8 = 0;
+    s.high.uint8 = 255;
+    v->observation_types.push_back(s);
+
+    memset(&s, 0, sizeof(s));
+    strcpy(s.name, "action");
+    s.scalar_type = LIBENV_SCALAR_TYPE_DISCRETE;
+    s.dtype = LIBENV_DTYPE_INT32;
+    s.ndim = 0;
+    s.low.int32 = 0;
+    s.high.int32 = v->num_actions - 1;
+    v->action_types.push_back(s);
+
+    const char *info_names[3] = {"prev_level_seed", "prev_level_complete", "level_seed"};
+    for (int i = 0; i < 3; i++) {
+        memset(&s, 0, sizeof(s));
+        strcpy(s.name, info_names[i]);
+        s.scalar_type = LIBENV_SCALAR_TYPE_DISCRETE;
+        s.ndim = 0;
+        if (i == 1) {
+            s.dtype = LIBENV_DTYPE_UINT8;
+            s.low.uint8 = 0;
+            s.high.uint8 = 1;
+        } else {
+            s.dtype = LIBENV_DTYPE_INT32;
+            s.low.int32 = 0;
+            s.high.int32 = INT32_MAX;
+        }
+        v->info_types.push_back(s);
+    }
+}
+
+}  // namespace
+
+// ================================================================= C ABI
+extern "C" {
+
+int libenv_version(void) { return LIBENV_VERSION; }
+
+int pgb200_is_device_build(void) {
+#ifndef PG_HOSTSIM
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
+    OptParser opts(options);
+    VecEnv *v = new VecEnv;
+    v->num_envs = num_envs;
+
+    // ---- VecGame::VecGame options (vecgame.cpp:169-190)
+    std::string env_name, resource_root;
+    int32_t num_levels = 0, start_level = -1, rand_seed = 0, num_threads = 4;
+    bool render_human = false;
+    opts.consume_string("env_name", &env_name);
+    opts.consume_int("num_levels", &num_levels);
+    opts.consume_int("start_level", &start_level);
+    opts.consume_int("num_actions", &v->num_actions);
+    opts.consume_int("rand_seed", &rand_seed);
+    opts.consume_int("num_threads", &num_threads);
+    opts.consume_string("resource_root", &resource_root);
+    opts.consume_bool("render_human", &render_human);
+    // ---- backend extensions
+    int32_t cuda_device = -1, env_index_offset = 0, env_index_total = -1;
+    bool snap = true;
+    opts.consume_int("cuda_device", &cuda_device);
+    opts.consume_int("env_index_offset", &env_index_offset);
+    opts.consume_int("env_index_total", &env_index_total);
+    opts.consume_bool("snap_target_rect", &snap);
+    if (env_index_total < 0)
+        env_index_total = env_index_offset + num_envs;
+
+    pg_fassert(num_threads >= 0);
+    pg_fassert(env_name != "");
+    pg_fassert(v->num_actions > 0);
+    pg_fassert(num_levels >= 0);
+    pg_fassert(start_level >= 0);
+    if (render_human)
+        pg_fatal("render_human (512x512 antialiased info['rgb']) is not supported by procgen_b200\n");
+
+    // ---- Game::parse_options (game.cpp:42-75)
+    bool use_easy_jump = false, paint_vel_info = false, use_generated_assets = false, use_monochrome_assets = false;
+    bool restrict_themes = false, use_backgrounds = true, center_agent = false, use_sequential_levels = false;
+    opts.consume_bool("use_easy_jump", &use_easy_jump);
+    opts.consume_bool("paint_vel_info", &paint_vel_info);
+    opts.consume_bool("use_generated_assets", &use_generated_assets);
+    opts.consume_bool("use_monochrome_assets", &use_monochrome_assets);
+    opts.consume_bool("restrict_themes", &restrict_themes);
+    opts.consume_bool("use_backgrounds", &use_backgrounds);
+    opts.consume_bool("center_agent", &center_agent);
+    opts.consume_bool("use_sequential_levels", &use_sequential_levels);
+    int32_t dist_mode = EasyMode, plain_assets = 0, physics_mode = 0, debug_mode = 0, game_type = 0;
+    opts.consume_int("distribution_mode", &dist_mode);
+    opts.consume_int("plain_assets", &plain_assets);
+    opts.consume_int("physics_mode", &physics_mode);
+    opts.consume_int("debug_mode", &debug_mode);
+    opts.consume_int("game_type", &game_type);
+    opts.ensure_empty();
+    if (use_generated_assets)
+        pg_fatal("use_generated_assets is not supported by procgen_b200\n");
+    if (use_monochrome_assets || paint_vel_info)
+        pg_fatal("use_monochrome_assets / paint_vel_info are not supported by procgen_b200 yet\n");
+
+    std::vector<std::string> env_names = split(env_name, ",");
+    const int G = (int)env_names.size();
+    pg_fassert(num_envs % G == 0);
+    pg_fassert(env_index_offset % G == 0);
+    for (const auto &name : env_names) {
+        const GameVTable *g = find_game(name);
+        if (!g)
+            pg_fatal("unknown or not yet supported env_name '%s'\n", name.c_str());
+        // mode validity, game.cpp:56-66
+        if (dist_mode == EasyMode || dist_mode == HardMode) {
+        } else if (dist_mode == ExtremeMode) {
+            pg_fassert(name == "chaser" || name == "dodgeball" || name == "leaper" || name == "starpilot");
+        } else if (dist_mode == MemoryMode) {
+            pg_fassert(name == "caveflyer" || name == "dodgeball" || name == "heist" || name == "jumper" || name == "maze" || name == "miner");
+        } else {
+            pg_fatal("invalid distribution_mode %d\n", dist_mode);
+        }
+        v->games.push_back(g);
+    }
+
+    // ---- device
+#ifndef PG_HOSTSIM
+    if (cuda_device < 0)
+        CUDA_CHECK(cudaGetDevice(&cuda_device));
+    v->device = cuda_device;
+    v->set_device();
+    CUDA_CHECK(cudaStreamCreateWithFlags(&v->own_stream, cudaStreamNonBlocking));
+    v->stream = v->own_stream;
+    // sub_step <-> push_obj recurse to depth 5 on the logic thread
+    CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+#else
+    v->device = -1;
+#endif
+
+    // ---- assets
+    std::string pack_path = resource_root;
+    if (pack_path.size() >= 5 && pack_path.compare(pack_path.size() - 5, 5, ".pack") == 0) {
+    } else if (!pack_path.empty()) {
+        if (pack_path.back() != '/')
+            pack_path += "/";
+        pack_path += "assets.pack";
+    } else {
+        pack_path = default_pack_path();
+    }
+    try {
+        host::AssetPackReader pack(pack_path);
+        host::AtlasBuilder atlas(pack);
+        std::vector<GameAssets> tables(G);
+        for (int g = 0; g < G; g++) atlas.build_game(v->games[g]->id, tables[g]);
+        v->d_atlas = dev_alloc<uint32_t>(atlas.texels.size());
+        copy_to_dev(v->d_atlas, atlas.texels.data(), atlas.texels.size() * sizeof(uint32_t));
+        for (int g = 0; g < G; g++) {
+            GameAssets *d = dev_alloc<GameAssets>(1);
+            copy_to_dev(d, &tables[g], sizeof(GameAssets));
+            v->d_assets.push_back(d);
+        }
+    } catch (const std::exception &e) {
+        pg_fatal("failed to load images %s\n", e.what());
+    }
+
+    fill_tensortypes(v);
+
+    // ---- state arrays
+    int ent_cap = 0, grid_cap = 0, scratch_words = 0;
+    for (auto g : v->games) {
+        ent_cap = std::max(ent_cap, g->ent_cap);
+        grid_cap = std::max(grid_cap, g->grid_cap);
+        scratch_words = std::max(scratch_words, g->scratch_words);
+    }
+    KParams &p = v->base;
+    const size_t N = (size_t)num_envs;
+    p.ent_stride = ent_cap + 1;
+    p.grid_stride = grid_cap;
+    p.scratch_stride = scratch_words;
+    p.hdr = dev_alloc<EnvHdr>(N);
+    p.ents = dev_alloc<Entity>(N * p.ent_stride);
+    p.grid = dev_alloc<int16_t>(N * p.grid_stride);
+    p.rng = dev_alloc<MT19937>(N);
+    p.lvl_rng = dev_alloc<MT19937>(N);
+    p.scratch = dev_alloc<int32_t>(N * (size_t)scratch_words);
+    p.atlas = v->d_atlas;
+    v->d_action = dev_alloc<int32_t>(N);
+    p.action = v->d_action;
+    p.rgb = dev_alloc<uint8_t>(N * RES_W * RES_H * 3);
+    p.rew = dev_alloc<float>(N);
+    p.first = dev_alloc<uint8_t>(N);
+    p.info_prev_level_seed = dev_alloc<int32_t>(N);
+    p.info_prev_level_complete = dev_alloc<uint8_t>(N);
+    p.info_level_seed = dev_alloc<int32_t>(N);
+
+    // ---- per-env seed chain (vecgame.cpp:301-314), replayed for the global env indices
+    {
+        std::mt19937 game_level_seed_gen;
+        game_level_seed_gen.seed((uint32_t)rand_seed);
+        for (int i = 0; i < env_index_offset; i++) (void)game_level_seed_gen();
+        std::vector<uint32_t> seeds(N);
+        for (size_t i = 0; i < N; i++) seeds[i] = (uint32_t)game_level_seed_gen();
+        v->d_lvl_seeds = dev_alloc<uint32_t>(N);
+        copy_to_dev(v->d_lvl_seeds, seeds.data(), N * sizeof(uint32_t));
+        p.lvl_seeds = v->d_lvl_seeds;
+    }
+
+    // vecgame.cpp:284-293
+    if (num_levels == 0) {
+        p.level_seed_low = 0;
+        p.level_seed_high = INT32_MAX;
+    } else {
+        p.level_seed_low = start_level;
+        p.level_seed_high = start_level + num_levels;
+    }
+    memset(&p.options, 0, sizeof(p.options));
+    p.options.paint_vel_info = paint_vel_info;
+    p.options.use_generated_assets = use_generated_assets;
+    p.options.use_monochrome_assets = use_monochrome_assets;
+    p.options.restrict_themes = restrict_themes;
+    p.options.use_backgrounds = use_backgrounds;
+    p.options.center_agent = center_agent;
+    p.options.use_sequential_levels = use_sequential_levels;
+    p.options.debug_mode = debug_mode;
+    p.options.distribution_mode = dist_mode;
+    p.snap = snap ? 1 : 0;
+    p.env_global_offset = env_index_offset;
+    return (libenv_env *)v;
+}
+
+int libenv_get_tensortypes(libenv_env *handle, enum libenv_space_name name, struct libenv_tensortype *out_types) {
+    VecEnv *v = (VecEnv *)handle;
+    const std::vector<libenv_tensortype> *types = nullptr;
+    if (name == LIBENV_SPACE_OBSERVATION)
+        types = &v->observation_types;
+    else if (name == LIBENV_SPACE_ACTION)
+        types = &v->action_types;
+    else if (name == LIBENV_SPACE_INFO)
+        types = &v->info_types;
+    else
+        return 0;
+    if (out_types)
+        for (size_t i = 0; i < types->size(); i++) out_types[i] = (*types)[i];
+    return (int)types->size();
+}
+
+static void *host_alloc(size_t bytes) {
+#ifndef PG_HOSTSIM
+    void *ptr = nullptr;
+    CUDA_CHECK(cudaHostAlloc(&ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return ptr;
+#else
+    return malloc(bytes ? bytes : 1);
+#endif
+}
+static void host_free(void *ptr) {
+#ifndef PG_HOSTSIM
+    if (ptr)
+        cudaFreeHost(ptr);
+#else
+    free(ptr);
+#endif
+}
+
+static void fetch_to_host(VecEnv *v) {
+    const size_t N = (size_t)v->num_envs;
+    const KParams &p = v->base;
+    const size_t frame = RES_W * RES_H * 3;
+    uint8_t *rgb_dst = v->ob_direct ? (uint8_t *)v->h_ob[0] : v->st_rgb;
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMemcpyAsync(rgb_dst, p.rgb, N * frame, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_CHECK(cudaMemcpyAsync(v->st_rew, p.rew, N * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
+    CUDA_CHECK(cudaMemcpyAsync(v->st_first, p.first, N, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_CHECK(cudaMemcpyAsync(v->st_prev_seed, p.info_prev_level_seed, N * 4, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_CHECK(cudaMemcpyAsync(v->st_prev_complete, p.info_prev_level_complete, N, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_CHECK(cudaMemcpyAsync(v->st_seed, p.info_level_seed, N * 4, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_CHECK(cudaStreamSynchronize(v->stream));
+#else
+    memcpy(rgb_dst, p.rgb, N * frame);
+    memcpy(v->st_rew, p.rew, N * sizeof(float));
+    memcpy(v->st_first, p.first, N);
+    memcpy(v->st_prev_seed, p.info_prev_level_seed, N * 4);
+    memcpy(v->st_prev_complete, p.info_prev_level_complete, N);
+    memcpy(v->st_seed, p.info_level_seed, N * 4);
+#endif
+    if (!v->ob_direct)
+        for (size_t e = 0; e < N; e++) memcpy(v->h_ob[e], v->st_rgb + e * frame, frame);
+    memcpy(v->h_rew, v->st_rew, N * sizeof(float));
+    memcpy(v->h_first, v->st_first, N);
+    for (size_t e = 0; e < N; e++) {
+        *(int32_t *)v->h_info[0][e] = v->st_prev_seed[e];
+        *(uint8_t *)v->h_info[1][e] = v->st_prev_complete[e];
+        *(int32_t *)v->h_info[2][e] = v->st_seed[e];
+    }
+}
+
+void libenv_set_buffers(libenv_env *handle, struct libenv_buffers *bufs) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    const size_t N = (size_t)v->num_envs;
+    pg_fassert(!v->initial_reset_done);
+    v->h_ob.assign(bufs->ob, bufs->ob + N);  // one observation space
+    v->h_ac.assign(bufs->ac, bufs->ac + N);  // one action space
+    v->h_info.resize(v->info_types.size());
+    for (size_t s = 0; s < v->info_types.size(); s++) v->h_info[s].assign(bufs->info + s * N, bufs->info + (s + 1) * N);
+    v->h_rew = bufs->rew;
+    v->h_first = bufs->first;
+    v->have_host_bufs = true;
+    {
+        // gym3 hands out one contiguous [N][64][64][3] array: page-lock it once and DMA into it
+        // directly instead of bouncing 12 KiB/env through a staging buffer every step
+        const size_t frame = RES_W * RES_H * 3;
+        bool contiguous = true;
+        for (size_t e = 1; e < N && contiguous; e++)
+            contiguous = ((uint8_t *)v->h_ob[e] == (uint8_t *)v->h_ob[0] + e * frame);
+        v->ob_direct = false;
+#ifndef PG_HOSTSIM
+        if (contiguous) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, v->h_ob[0]) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+                v->ob_direct = true;
+            } else {
+                cudaGetLastError();
+                if (cudaHostRegister(v->h_ob[0], N * frame, cudaHostRegisterDefault) == cudaSuccess) {
+                    v->ob_direct = true;
+                    v->ob_registered = true;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
+#else
+        v->ob_direct = contiguous;
+#endif
+    }
+    v->st_rgb = v->ob_direct ? nullptr : (uint8_t *)host_alloc(N * RES_W * RES_H * 3);
+    v->st_action = (int32_t *)host_alloc(N * 4);
+    v->st_rew = (float *)host_alloc(N * 4);
+    v->st_first = (uint8_t *)host_alloc(N);
+    v->st_prev_seed = (int32_t *)host_alloc(N * 4);
+    v->st_prev_complete = (uint8_t *)host_alloc(N);
+    v->st_seed = (int32_t *)host_alloc(N * 4);
+    v->ensure_initial_reset();  // vecgame.cpp:349-353
+}
+
+void libenv_observe(libenv_env *handle) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    pg_fassert(v->have_host_bufs);
+    fetch_to_host(v);
+}
+
+void libenv_act(libenv_env *handle) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    pg_fassert(v->have_host_bufs);
+    const size_t N = (size_t)v->num_envs;
+    v->sync();  // staging buffer reuse (wait_for_stepping_threads, vecgame.cpp:379)
+    for (size_t e = 0; e < N; e++) v->st_action[e] = *(int32_t *)v->h_ac[e];
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMemcpyAsync(v->d_action, v->st_action, N * 4, cudaMemcpyHostToDevice, v->stream));
+#else
+    memcpy(v->d_action, v->st_action, N * 4);
+#endif
+    v->launch(false);
+}
+
+void libenv_close(libenv_env *handle) {
+    VecEnv *v = (VecEnv *)handle;
+    if (!v)
+        return;
+    v->set_device();
+    v->sync();
+    KParams &p = v->base;
+    dev_free(p.hdr);
+    dev_free(p.ents);
+    dev_free(p.grid);
+    dev_free(p.rng);
+    dev_free(p.lvl_rng);
+    dev_free(p.scratch);
+    dev_free(v->d_atlas);
+    dev_free(v->d_action);
+    dev_free(p.rgb);
+    dev_free(p.rew);
+    dev_free(p.first);
+    dev_free(p.info_prev_level_seed);
+    dev_free(p.info_prev_level_complete);
+    dev_free(p.info_level_seed);
+    dev_free(v->d_lvl_seeds);
+    for (auto a : v->d_assets) dev_free(a);
+    host_free(v->st_rgb);
+#ifndef PG_HOSTSIM
+    if (v->ob_registered)
+        cudaHostUnregister(v->h_ob[0]);
+#endif
+    host_free(v->st_action);
+    host_free(v->st_rew);
+    host_free(v->st_first);
+    host_free(v->st_prev_seed);
+    host_free(v->st_prev_complete);
+    host_free(v->st_seed);
+#ifndef PG_HOSTSIM
+    if (v->own_stream)
+        cudaStreamDestroy(v->own_stream);
+#endif
+    delete v;
+}
+
+int pgb200_get_device_buffers(libenv_env *handle, struct pgb200_device_buffers *out) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->ensure_initial_reset();
+    const KParams &p = v->base;
+    out->rgb = p.rgb;
+    out->rew = p.rew;
+    out->first = p.first;
+    out->prev_level_seed = p.info_prev_level_seed;
+    out->prev_level_complete = p.info_prev_level_complete;
+    out->level_seed = p.info_level_seed;
+    out->action = v->d_action;
+    out->num_envs = v->num_envs;
+    out->device = v->device;
+#ifndef PG_HOSTSIM
+    out->stream = (void *)v->stream;
+#else
+    out->stream = nullptr;
+#endif
+    return 0;
+}
+
+void pgb200_set_stream(libenv_env *handle, void *stream) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+#ifndef PG_HOSTSIM
+    v->stream = stream ? (cudaStream_t)stream : v->own_stream;
+#else
+    (void)stream;
+#endif
+}
+
+void pgb200_act_device(libenv_env *handle) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->ensure_initial_reset();
+    v->launch(false);
+}
+
+void pgb200_sync(libenv_env *handle) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+}
+
+uint32_t pgb200_get_errors(libenv_env *handle, uint32_t *host_out) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+    const size_t N = (size_t)v->num_envs;
+    std::vector<EnvHdr> hdr(N);
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMemcpy(hdr.data(), v->base.hdr, N * sizeof(EnvHdr), cudaMemcpyDeviceToHost));
+#else
+    memcpy(hdr.data(), v->base.hdr, N * sizeof(EnvHdr));
+#endif
+    uint32_t any = 0;
+    for (size_t e = 0; e < N; e++) {
+        if (host_out)
+            host_out[e] = hdr[e].err;
+        any |= hdr[e].err;
+    }
+    return any;
+}
+
+int64_t pgb200_kernel_launches(libenv_env *handle) { return ((VecEnv *)handle)->launches; }
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+"""ProcgenGym3Env on B200 — host-side mirror of the reference's Python boundary.
+
+Mirrors ``procgen/env.py``: ``BaseProcgenEnv`` (:66-200) + ``ProcgenGym3Env`` (:203-246) with the same
+constructor keywords, defaults, option marshalling and the gym3 ``Env`` surface callers use
+(``num``, ``ob_space``, ``ac_space``, ``observe()``, ``act()``, ``get_info()``, ``callmethod()``).
+Differences, all on purpose:
+
+* ``observe()`` returns ``torch.cuda`` tensors that alias the library's HBM buffers (no copy, no
+  host round trip); ``act()`` accepts a CUDA tensor (stays on device) or anything array-like.
+* ``host_buffers=True`` selects the reference's exact contract instead: numpy buffers owned by
+  the caller, filled through ``libenv_set_buffers/act/observe`` like gym3's ``CEnv`` does.
+* ``shard=(rank, world_size)`` makes this handle own envs ``[rank*num, (rank+1)*num)`` of one
+  logical ``world_size*num``-env VecGame (same per-env seed chain, vecgame.cpp:301-314);
+  ``gather_observations()`` is the single NCCL gather of SURVEY §8(e).
+
+gym3 is not installable here, so the few space types used are defined below with gym3's names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import random
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import libenv as L
+
+MAX_STATE_SIZE = 2 ** 20  # env.py:12
+
+ENV_NAMES = [  # env.py:14-31
+    "bigfish", "bossfight", "caveflyer", "chaser", "climber", "coinrun", "dodgeball", "fruitbot",
+    "heist", "jumper", "leaper", "maze", "miner", "ninja", "plunder", "starpilot",
+]
+
+EXPLORATION_LEVEL_SEEDS = {  # env.py:33-42
+    "coinrun": 1949448038, "caveflyer": 1259048185, "leaper": 1318677581, "jumper": 1434825276,
+    "maze": 158988835, "heist": 876640971, "climber": 1561126160, "ninja": 1123500215,
+}
+
+DISTRIBUTION_MODE_DICT = {"easy": 0, "hard": 1, "extreme": 2, "memory": 10, "exploration": 20}  # env.py:45-51
+
+
+# ---- the slice of gym3.types the reference's callers touch
+@dataclass(frozen=True)
+class Discrete:
+    n: int
+    dtype_name: str = "int32"
+
+
+@dataclass(frozen=True)
+class TensorType:
+    eltype: Discrete
+    shape: Tuple[int, ...]
+
+
+class DictType(dict):
+    pass
+
+
+def create_random_seed():
+    """env.py:54-63 (mpi4py de-correlation becomes torch.distributed rank de-correlation)."""
+    rand_seed = random.SystemRandom().randint(0, 2 ** 31 - 1)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            rand_seed = rand_seed - (rand_seed % dist.get_world_size()) + dist.get_rank()
+    except Exception:
+        pass
+    return rand_seed
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so torch can alias library-owned HBM."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class BaseProcgenEnv:
+    """env.py:66-200."""
+
+    def __init__(self, num, env_name, options, debug=False, rand_seed=None, num_levels=0, start_level=0,
+                 use_sequential_levels=False, debug_mode=0, resource_root=None, num_threads=4, render_mode=None,
+                 host_buffers=False, device=None, shard=None, snap_target_rect=True, lib_path=None):
+        self._lib = L.load(lib_path)
+        self.combos = self.get_combos()
+        if render_mode is None:
+            render_human = False
+        elif render_mode == "rgb_array":
+            render_human = True
+        else:
+            raise Exception(f"invalid render mode {render_mode}")
+        if render_human:
+            raise NotImplementedError("render_mode='rgb_array' (512x512 antialiased info['rgb']) is out of scope")
+        if rand_seed is None:
+            rand_seed = create_random_seed()
+        if resource_root is None:
+            resource_root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data") + os.sep
+
+        options = dict(options)
+        options.update({
+            "env_name": env_name,
+            "num_levels": num_levels,
+            "start_level": start_level,
+            "num_actions": len(self.combos),
+            "use_sequential_levels": bool(use_sequential_levels),
+            "debug_mode": debug_mode,
+            "rand_seed": rand_seed,
+            "num_threads": num_threads,
+            "render_human": render_human,
+            "resource_root": resource_root,
+        })
+        self._host_buffers = bool(host_buffers)
+        self._torch = None
+        if self._lib.pgb200_is_device_build():
+            import torch
+
+            self._torch = torch
+            if not torch.cuda.is_available():
+                raise RuntimeError("procgen_b200 needs a CUDA device (there is no CPU fallback)")
+            if device is None:
+                device = torch.cuda.current_device()
+            device = torch.device(device).index if not isinstance(device, int) else device
+            options["cuda_device"] = int(device)
+        self.device_index = device
+        if shard is not None:
+            rank, world = shard
+            options["env_index_offset"] = int(rank) * int(num)
+            options["env_index_total"] = int(world) * int(num)
+        self.shard = shard
+        if not snap_target_rect:
+            options["snap_target_rect"] = False
+        self.options = options
+        self.num = int(num)
+
+        self._keep = []
+        self._h = self._lib.libenv_make(self.num, L.make_options(self._keep, options))
+        if not self._h:
+            raise RuntimeError("libenv_make failed")
+
+        # spaces (vecgame.cpp:212-268); the action space is unwrapped like env.py:138
+        self.ob_space = DictType(rgb=TensorType(Discrete(256, "uint8"), (64, 64, 3)))
+        self.ac_space = TensorType(Discrete(len(self.combos), "int32"), ())
+        self._info_names = ["prev_level_seed", "prev_level_complete", "level_seed"]
+
+        if self._host_buffers:
+            self._setup_host_buffers()
+        else:
+            self._setup_device_buffers()
+
+    # ------------------------------------------------------------------ buffer plumbing
+    def _setup_host_buffers(self):
+        n = self.num
+        self._rgb = np.zeros((n, 64, 64, 3), np.uint8)
+        self._rew = np.zeros(n, np.float32)
+        self._first = np.zeros(n, np.uint8)
+        self._ac = np.zeros(n, np.int32)
+        self._info = {"prev_level_seed": np.zeros(n, np.int32), "prev_level_complete": np.zeros(n, np.uint8),
+                      "level_seed": np.zeros(n, np.int32)}
+        ob_ptrs = (C.c_void_p * n)(*[self._rgb.ctypes.data + e * 64 * 64 * 3 for e in range(n)])
+        ac_ptrs = (C.c_void_p * n)(*[self._ac.ctypes.data + e * 4 for e in range(n)])
+        info_ptrs = (C.c_void_p * (3 * n))()
+        for si, name in enumerate(self._info_names):
+            arr = self._info[name]
+            for e in range(n):
+                info_ptrs[si * n + e] = arr.ctypes.data + e * arr.itemsize
+        self._bufs = L.Buffers(ob_ptrs, self._rew.ctypes.data_as(C.POINTER(C.c_float)),
+                               self._first.ctypes.data_as(C.POINTER(C.c_uint8)), info_ptrs, ac_ptrs)
+        self._keep += [ob_ptrs, ac_ptrs, info_ptrs]
+        self._lib.libenv_set_buffers(self._h, C.byref(self._bufs))
+
+    def _setup_device_buffers(self):
+        torch = self._torch
+        if torch is None:
+            raise RuntimeError("device-resident buffers need the CUDA build")
+        dev = torch.device("cuda", self.device_index)
+        with torch.cuda.device(dev):
+            self._stream_handle = torch.cuda.current_stream(dev).cuda_stream
+            self._lib.pgb200_set_stream(self._h, C.c_void_p(self._stream_handle))
+            db = L.DeviceBuffers()
+            rc = self._lib.pgb200_get_device_buffers(self._h, C.byref(db))
+            if rc != 0:
+                raise RuntimeError("pgb200_get_device_buffers failed")
+            n = self.num
+
+            def alias(ptr, shape, typestr):
+                return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=dev)
+
+            self._rgb = alias(db.rgb, (n, 64, 64, 3), "|u1")
+            self._rew = alias(db.rew, (n,), "<f4")
+            self._first = alias(db.first, (n,), "|u1")
+            self._ac = alias(db.action, (n,), "<i4")
+            self._info = {"prev_level_seed": alias(db.prev_level_seed, (n,), "<i4"),
+                          "prev_level_complete": alias(db.prev_level_complete, (n,), "|u1"),
+                          "level_seed": alias(db.level_seed, (n,), "<i4")}
+        self._dev = dev
+        self._pinned_ac = None
+
+    # ------------------------------------------------------------------ gym3 Env surface
+    def observe(self):
+        """-> (rew f32[N], {"rgb": u8[N,64,64,3]}, first bool[N]); device tensors unless host_buffers."""
+        if self._host_buffers:
+            self._lib.libenv_observe(self._h)
+            return self._rew, {"rgb": self._rgb}, self._first.astype(bool)
+        return self._rew, {"rgb": self._rgb}, self._first.bool()
+
+    def act(self, ac):
+        """env.py:197-200: actions are cast to int32. Asynchronous, like VecGame::act."""
+        if self._host_buffers:
+            self._ac[:] = np.asarray(ac).astype(np.int32)
+            self._lib.libenv_act(self._h)
+            return
+        torch = self._torch
+        with torch.cuda.device(self._dev):
+            # keep every launch on the caller's current stream
+            cur = torch.cuda.current_stream(self._dev).cuda_stream
+            if cur != self._stream_handle:
+                self._lib.pgb200_set_stream(self._h, C.c_void_p(cur))
+                self._stream_handle = cur
+            if torch.is_tensor(ac) and ac.is_cuda:
+                self._ac.copy_(ac.to(torch.int32), non_blocking=True)
+            else:
+                host = torch.as_tensor(np.asarray(ac).astype(np.int32))
+                if self._pinned_ac is None:
+                    self._pinned_ac = torch.empty(self.num, dtype=torch.int32, pin_memory=True)
+                self._pinned_ac.copy_(host)
+                self._ac.copy_(self._pinned_ac, non_blocking=True)
+            self._lib.pgb200_act_device(self._h)
+
+    def get_info(self) -> List[dict]:
+        if self._host_buffers:
+            cols = {k: v for k, v in self._info.items()}
+        else:
+            cols = {k: v.cpu().numpy() for k, v in self._info.items()}
+        return [{k: cols[k][i] for k in self._info_names} for i in range(self.num)]
+
+    def get_info_tensors(self):
+        """Column form of get_info() without a host copy."""
+        return dict(self._info)
+
+    def callmethod(self, method: str, *args, **kwargs):
+        return getattr(self, method)(*args, **kwargs)
+
+    def get_state(self):
+        raise NotImplementedError("get_state/set_state wire format: SURVEY §8(f) item 1, not built yet")
+
+    def set_state(self, states):
+        raise NotImplementedError("get_state/set_state wire format: SURVEY §8(f) item 1, not built yet")
+
+    def get_combos(self):  # env.py:155-172
+        return [("LEFT", "DOWN"), ("LEFT",), ("LEFT", "UP"), ("DOWN",), (), ("UP",), ("RIGHT", "DOWN"), ("RIGHT",),
+                ("RIGHT", "UP"), ("D",), ("A",), ("W",), ("S",), ("Q",), ("E",)]
+
+    def keys_to_act(self, keys_list: Sequence[Sequence[str]]) -> List[Optional[np.ndarray]]:  # env.py:174-195
+        result = []
+        for keys in keys_list:
+            action = None
+            max_len = -1
+            for i, combo in enumerate(self.get_combos()):
+                pressed = all(key in keys for key in combo)
+                if pressed and (max_len < len(combo)):
+                    action = i
+                    max_len = len(combo)
+            if action is not None:
+                action = np.array([action])
+            result.append(action)
+        return result
+
+    # ------------------------------------------------------------------ B200 extras
+    def sync(self):
+        self._lib.pgb200_sync(self._h)
+
+    def errors(self) -> int:
+        """OR of the per-env sticky error bits (0 = healthy)."""
+        return int(self._lib.pgb200_get_errors(self._h, None))
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.pgb200_kernel_launches(self._h))
+
+    def gather_observations(self, dst: int = 0):
+        """The only collective on this path: NCCL gather of this rank's rgb shard to `dst`.
+        Returns u8[world*num,64,64,3] on dst, None elsewhere."""
+        import torch.distributed as dist
+
+        torch = self._torch
+        world = dist.get_world_size()
+        if dist.get_rank() == dst:
+            out = torch.empty((world * self.num, 64, 64, 3), dtype=torch.uint8, device=self._dev)
+            dist.gather(self._rgb, list(out.chunk(world, dim=0)), dst=dst)
+            return out
+        dist.gather(self._rgb, None, dst=dst)
+        return None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.libenv_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ProcgenGym3Env(BaseProcgenEnv):
+    """env.py:203-246 — same keywords and defaults."""
+
+    def __init__(self, num, env_name, center_agent=True, use_backgrounds=True, use_monochrome_assets=False,
+                 restrict_themes=False, use_generated_assets=False, paint_vel_info=False, distribution_mode="hard",
+                 **kwargs):
+        assert distribution_mode in DISTRIBUTION_MODE_DICT, f'"{distribution_mode}" is not a valid distribution mode.'
+        if distribution_mode == "exploration":
+            assert env_name in EXPLORATION_LEVEL_SEEDS, f"{env_name} does not support exploration mode"
+            distribution_mode = DISTRIBUTION_MODE_DICT["hard"]
+            assert "num_levels" not in kwargs, "exploration mode overrides num_levels"
+            kwargs["num_levels"] = 1
+            assert "start_level" not in kwargs, "exploration mode overrides start_level"
+            kwargs["start_level"] = EXPLORATION_LEVEL_SEEDS[env_name]
+        else:
+            distribution_mode = DISTRIBUTION_MODE_DICT[distribution_mode]
+        options = {
+            "center_agent": bool(center_agent),
+            "use_generated_assets": bool(use_generated_assets),
+            "use_monochrome_assets": bool(use_monochrome_assets),
+            "restrict_themes": bool(restrict_themes),
+            "use_backgrounds": bool(use_backgrounds),
+            "paint_vel_info": bool(paint_vel_info),
+            "distribution_mode": distribution_mode,
+        }
+        super().__init__(num, env_name, options, **kwargs)

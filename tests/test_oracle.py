@@ -1,0 +1,67 @@
+"""Pins the oracle (reference sources compiled in place + raster restatement) before it is trusted:
+known-answer values recorded from the unmodified reference logic and the committed
+golden fixtures in tests/golden/."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle.ref_env import RefVecEnv, mt19937_actions
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_mt19937_known_answers():
+    # std::mt19937 seed 0 -> 2357136044, 2546248239, 3071714933
+    rs = np.random.RandomState(0)
+    assert list(rs.randint(0, 2 ** 32, size=3, dtype=np.uint32)) == [2357136044, 2546248239, 3071714933]
+
+
+def test_initial_level_seeds(ref_lib, asset_pack):
+    env = RefVecEnv(8, "coinrun", distribution_mode="easy", num_levels=200, start_level=0, rand_seed=0)
+    rew, ob, first = env.observe()
+    assert list(env.info["level_seed"]) == [71, 106, 137, 26, 171, 23, 156, 72]
+    assert first.all() and (rew == 0).all()
+    env.close()
+
+
+@pytest.mark.parametrize("name,mode,n,steps,expect", [
+    ("coinrun", "easy", 64, 1000, (360.0, 95, 36)),
+    ("coinrun", "hard", 4, 500, (0.0, 1, 0)),
+    ("bigfish", "hard", 64, 1000, (128.0, 525, 0)),
+    ("maze", "hard", 64, 1000, (600.0, 143, 60)),
+    ("heist", "hard", 64, 1000, (120.0, 66, 12)),
+])
+def test_aggregate_known_answers(ref_lib, asset_pack, name, mode, n, steps, expect):
+    """(sum reward, episode starts, level completes) under the §8c action recipe."""
+    env = RefVecEnv(n, name, distribution_mode=mode, num_levels=200, start_level=0, rand_seed=0)
+    acts = mt19937_actions(0, n, steps)
+    tot, starts, comp = 0.0, 0, 0
+    env.observe()
+    for t in range(steps):
+        env.act(acts[t])
+        rew, ob, first = env.observe()
+        tot += float(rew.sum())
+        starts += int(first.sum())
+        comp += int(env.info["prev_level_complete"].sum())
+    env.close()
+    assert (tot, starts, comp) == expect
+
+
+@pytest.mark.parametrize("fixture", sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz")) if os.path.isdir(GOLDEN) else [])
+def test_oracle_reproduces_golden(ref_lib, asset_pack, fixture):
+    g = np.load(os.path.join(GOLDEN, fixture), allow_pickle=False)
+    kw = dict(distribution_mode=str(g["mode"]), num_levels=int(g["num_levels"]), start_level=0, rand_seed=int(g["rand_seed"]))
+    env = RefVecEnv(int(g["num"]), str(g["env_name"]), **kw)
+    acts = g["actions"]
+    env.observe()
+    for t in range(acts.shape[0]):
+        env.act(acts[t])
+        rew, ob, first = env.observe()
+        assert np.array_equal(rew, g["rew"][t])
+        assert np.array_equal(first, g["first"][t])
+        assert np.array_equal(env.info["level_seed"], g["level_seed"][t])
+        assert hashlib.sha256(ob["rgb"].tobytes()).hexdigest() == str(g["rgb_sha256"][t])
+    assert np.array_equal(ob["rgb"], g["last_rgb"])
+    env.close()
