@@ -92,33 +92,58 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(game, mode, budget_s=15.0, n_envs=None, threads=None):
-    """Times oracle/_ref on the host cores on a bounded sample of the same workload."""
+def cpu_reference_rate(game, mode, budget_s=15.0, envs_per_worker=64, workers=None):
+    """Times oracle/_ref on ALL host cores on a bounded sample of the same workload.
+
+    The reference scales across cores by running independent VecGames (its own thread pool is one
+    mutex + notify_all per game and gets slower with threads for cheap steps), so the
+    baseline is `workers` = nproc independent reference VecGames (num_threads=0, 64 envs each),
+    each driven by its own host thread (ctypes releases the GIL inside libenv_act/observe)."""
     import numpy as np
 
     from oracle.ref_env import RefVecEnv
 
     cores = os.cpu_count() or 1
-    threads = cores if threads is None else threads
-    n = n_envs or max(64, 64 * cores)
-    env = RefVecEnv(n, game, distribution_mode=mode, num_levels=0, start_level=0, rand_seed=0, num_threads=threads)
-    rng = np.random.RandomState(0)
-    env.observe()
-    for _ in range(3):
-        env.act(rng.randint(0, 15, size=n).astype(np.int32))
+    workers = cores if workers is None else workers
+    n = envs_per_worker
+    envs = [RefVecEnv(n, game, distribution_mode=mode, num_levels=0, start_level=0, rand_seed=w, num_threads=0)
+            for w in range(workers)]
+    counts = [0] * workers
+    start = threading.Barrier(workers + 1)
+    t_end = [0.0]
+
+    def work(w):
+        env = envs[w]
+        rng = np.random.RandomState(w)
+        acts = rng.randint(0, 15, size=(64, n)).astype(np.int32)
         env.observe()
-    steps = 0
+        for i in range(2):
+            env.act(acts[i])
+            env.observe()
+        start.wait()
+        i = 0
+        while time.perf_counter() < t_end[0]:
+            env.act(acts[i & 63])
+            env.observe()
+            i += 1
+        counts[w] = i
+
+    threads = [threading.Thread(target=work, args=(w,)) for w in range(workers)]
+    for t in threads:
+        t.start()
+    t_end[0] = time.perf_counter() + budget_s + 3600.0
+    start.wait()
     t0 = time.perf_counter()
-    while True:
-        env.act(rng.randint(0, 15, size=n).astype(np.int32))
-        env.observe()
-        steps += 1
-        el = time.perf_counter() - t0
-        if el >= budget_s or steps >= 100000:
-            break
-    env.close()
-    return n * steps / el, {"cores": threads, "sample": f"{n} envs x {steps} steps ({el:.1f}s), num_threads={threads}",
-                            "seconds": el, "env_steps": n * steps}
+    t_end[0] = t0 + budget_s
+    for t in threads:
+        t.join()
+    el = time.perf_counter() - t0
+    for e in envs:
+        e.close()
+    total = n * sum(counts)
+    return total / el, {"cores": workers, "sample": f"{workers} independent reference VecGames x {n} envs, {sum(counts)} "
+                        f"vec-steps total in {el:.1f}s (num_threads=0 each, one host thread per VecGame)",
+                        "seconds": el, "env_steps": total}
 
 
 def run_reference_arm(args):

@@ -147,7 +147,10 @@ LIBENV_API int pgb200_get_device_buffers(libenv_env *handle, struct pgb200_devic
 
 /* Re-home all subsequent work of this handle onto the caller's stream (a cudaStream_t, e.g. the
  * framework's current stream) so launches are ordered with the caller's own kernels and copies
- * without events. The handle's previous work is drained first. NULL restores the private stream. */
+ * without events. The handle's previous work is drained first. The value is used literally: NULL is
+ * CUDA's legacy default stream. A new handle starts on a private non-blocking stream;
+ * PGB200_PRIVATE_STREAM goes back to it. */
+#define PGB200_PRIVATE_STREAM ((void *)(intptr_t)-1)
 LIBENV_API void pgb200_set_stream(libenv_env *handle, void *stream);
 
 /* Steps every env with the actions currently in the device action buffer. Asynchronous: enqueues

@@ -120,6 +120,31 @@ PG_HD uint32_t pg_byte_mul(uint32_t x, uint32_t a) {
     return x | t;
 }
 
+// ---- warp-cooperative scan (logic kernel: one warp = one env, all 32 lanes run the serial game
+// logic redundantly and in lockstep — every load/store is warp-uniform — and split up only inside
+// these scans, which replace the reference's O(E) "for each entity, test" loops).
+// pg_scan_down(upper, pred): largest i in [0, upper) with pred(i), or -1. pred must be read-only.
+// Sequential semantics are preserved by the callers: they handle hit i, then rescan [0, i).
+template <class F>
+PG_HD int pg_scan_down(int upper, F pred) {
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31u);
+    for (int base = upper - 1; base >= 0; base -= 32) {
+        const int i = base - lane;
+        const bool hit = (i >= 0) && pred(i);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m)
+            return base - (__ffs((int)m) - 1);
+    }
+    return -1;
+#else
+    for (int i = upper - 1; i >= 0; i--)
+        if (pred(i))
+            return i;
+    return -1;
+#endif
+}
+
 // error bits latched per env (the reference would fassert/exit; we must not kill the GPU)
 enum ErrBits : uint32_t {
     ERR_ENTITY_OVERFLOW = 1u << 0,

@@ -91,16 +91,16 @@ template <class G>
 struct Engine {
     // ---- grid access (basic-abstract-game.cpp:167-218, grid.h)
     static PG_HD bool grid_contains(Ctx &c, int x, int y) {
-        return 0 <= y && y < c.h->main_height && 0 <= x && x < c.h->main_width;
+        return 0 <= y && y < c.mh && 0 <= x && x < c.mw;
     }
     static PG_HD int get_obj(Ctx &c, int x, int y) {
         if (!grid_contains(c, x, y))
-            return c.h->out_of_bounds_object;
-        return c.grid[y * c.h->main_width + x];
+            return c.oob;
+        return c.grid[y * c.mw + x];
     }
     static PG_HD int get_obj_idx(Ctx &c, int idx) {
-        if (!(0 <= idx && idx < c.h->main_width * c.h->main_height))
-            return c.h->out_of_bounds_object;
+        if (!(0 <= idx && idx < c.mw * c.mh))
+            return c.oob;
         return c.grid[idx];
     }
     static PG_HD void set_obj(Ctx &c, int x, int y, int v) {
@@ -108,10 +108,10 @@ struct Engine {
             c.h->err |= ERR_GRID_OOB;
             return;
         }
-        c.grid[y * c.h->main_width + x] = (int16_t)v;
+        c.grid[y * c.mw + x] = (int16_t)v;
     }
     static PG_HD void set_obj_idx(Ctx &c, int idx, int v) {
-        if (!(0 <= idx && idx < c.h->main_width * c.h->main_height)) {
+        if (!(0 <= idx && idx < c.mw * c.mh)) {
             c.h->err |= ERR_GRID_OOB;
             return;
         }
@@ -120,7 +120,7 @@ struct Engine {
     static PG_HD int to_grid_idx(Ctx &c, int x, int y) {
         if (!grid_contains(c, x, y))
             return INVALID_IDX;
-        return y * c.h->main_width + x;
+        return y * c.mw + x;
     }
     // basic-abstract-game.cpp:125-131 (elem travels through a `char`)
     static PG_HD void fill_elem(Ctx &c, int x, int y, int dx, int dy, int elem) {
@@ -132,14 +132,14 @@ struct Engine {
     // basic-abstract-game.cpp:167-174 — floor() is the double overload
     static PG_HD int get_obj_from_floats(Ctx &c, float i, float j) {
         if (i < 0)
-            return c.h->out_of_bounds_object;
+            return c.oob;
         if (j < 0)
-            return c.h->out_of_bounds_object;
+            return c.oob;
         return get_obj(c, (int)pg_dfloor((double)i), (int)pg_dfloor((double)j));
     }
     static PG_HD int get_agent_index(Ctx &c) {
         Entity &a = agent_of(c);
-        return int(a.y) * c.h->main_width + int(a.x);
+        return int(a.y) * c.mw + int(a.x);
     }
 
     // ---- entity list
@@ -165,8 +165,8 @@ struct Engine {
     }
     // basic-abstract-game.cpp:575-582
     static PG_HD int spawn_entity_at_idx(Ctx &c, int idx, float r, int type) {
-        float x = (idx % c.h->main_width) + .5;
-        float y = (idx / c.h->main_width) + .5;
+        float x = (idx % c.mw) + .5;
+        float y = (idx / c.mw) + .5;
         return add_entity(c, x, y, 0, 0, r, type);
     }
     // basic-abstract-game.cpp:225-231
@@ -192,19 +192,16 @@ struct Engine {
     }
     // basic-abstract-game.cpp:1114-1124
     static PG_HD bool has_any_collision(Ctx &c, const Entity &e1, float margin = 0) {
-        for (int i = c.h->n_ents - 1; i >= 0; i--) {
-            const Entity &ent = c.ents[i];
-            if (!ent.avoids_collisions && has_collision(e1, ent, margin))
-                return true;
-        }
-        return false;
+        const Entity *ents = c.ents;
+        return pg_scan_down(c.h->n_ents, [&](int i) {
+                   const Entity &ent = ents[i];
+                   return !ent.avoids_collisions && has_collision(e1, ent, margin);
+               }) >= 0;
     }
     // basic-abstract-game.cpp:520-528
     static PG_HD bool agent_has_collision(Ctx &c) {
-        for (int i = 0; i < c.h->n_ents; i++)
-            if (has_agent_collision(c, c.ents[i]))
-                return true;
-        return false;
+        Ctx *cp = &c;
+        return pg_scan_down(c.h->n_ents, [&](int i) { return has_agent_collision(*cp, cp->ents[i]); }) >= 0;
     }
     // basic-abstract-game.cpp:1068-1084
     static PG_HD bool is_out_of_bounds(Ctx &c, const Entity &e1) {
@@ -213,9 +210,9 @@ struct Engine {
             return true;
         if (y + ry < 0)
             return true;
-        if (x - rx > c.h->main_width)
+        if (x - rx > c.mw)
             return true;
-        if (y - ry > c.h->main_height)
+        if (y - ry > c.mh)
             return true;
         return false;
     }
@@ -389,32 +386,43 @@ struct Engine {
 
         bool block2 = false;
 
-        for (int i = c.h->n_ents - 1; i >= 0; i--) {
-            if (i == oi)
-                continue;
+        // reference: for i = n-1..0 { skip self/erased; if (has_collision) {...} } — the test runs
+        // warp-wide, the (rare) hits are handled one at a time in descending order, and the scan
+        // restarts below each hit because handling may have moved things.
+        int i = c.h->n_ents;
+        while (true) {
+            const Entity *ents = c.ents;
+            const float ox = obj.x, oy = obj.y, orx = obj.rx, ory = obj.ry;  // hoisted: warp-uniform
+            i = pg_scan_down(i, [&](int k) {
+                const Entity &mm = ents[k];
+                if (k == oi || mm.will_erase)
+                    return false;
+                // has_collision(obj, m, POS_EPS), basic-abstract-game.cpp:1145-1150
+                float threshold_x = (orx + mm.rx) + POS_EPS;
+                float threshold_y = (ory + mm.ry) + POS_EPS;
+                return (pg_dfabs((double)(ox - mm.x)) < (double)threshold_x) && (pg_dfabs((double)(oy - mm.y)) < (double)threshold_y);
+            });
+            if (i < 0)
+                break;
             Entity &m = c.ents[i];
-            if (m.will_erase)
-                continue;
             bool curr_block = false;
-            if (has_collision(obj, m, POS_EPS)) {
-                if (G::is_blocked_ents(c, oi, i, is_horizontal)) {
-                    curr_block = true;
-                } else if (G::will_reflect(c, obj.type, m.type)) {
-                    if (is_horizontal) {
-                        float delx = m.x - obj.x;
-                        float rsum = m.rx + obj.rx;
-                        obj.x += _vx > 0 ? -2 * (rsum - delx) : 2 * (rsum + delx);
-                        obj.vx = -1 * obj.vx;
-                    } else {
-                        float dely = m.y - obj.y;
-                        float rsum = m.ry + obj.ry;
-                        obj.y += _vy > 0 ? -2 * (rsum - dely) : 2 * (rsum + dely);
-                        obj.vy = -1 * obj.vy;
-                    }
+            if (G::is_blocked_ents(c, oi, i, is_horizontal)) {
+                curr_block = true;
+            } else if (G::will_reflect(c, obj.type, m.type)) {
+                if (is_horizontal) {
+                    float delx = m.x - obj.x;
+                    float rsum = m.rx + obj.rx;
+                    obj.x += _vx > 0 ? -2 * (rsum - delx) : 2 * (rsum + delx);
+                    obj.vx = -1 * obj.vx;
+                } else {
+                    float dely = m.y - obj.y;
+                    float rsum = m.ry + obj.ry;
+                    obj.y += _vy > 0 ? -2 * (rsum - dely) : 2 * (rsum + dely);
+                    obj.vy = -1 * obj.vy;
                 }
-                if (curr_block)
-                    push_obj(c, i, oi, is_horizontal, depth);
             }
+            if (curr_block)
+                push_obj(c, i, oi, is_horizontal, depth);
             block2 = block2 || curr_block;
         }
         return block || block2;
@@ -571,15 +579,30 @@ struct Engine {
 
         step_entities(c);
 
-        for (int i = h.n_ents - 1; i >= 0; i--) {
+        // collision pass (:719-741): entities that need any work are found warp-wide; each is then
+        // processed exactly as the reference's loop body, in descending order.
+        int i = h.n_ents;
+        while (true) {
+            Ctx *cp = &c;
+            i = pg_scan_down(i, [&](int k) {
+                const Entity &e = cp->ents[k];
+                return e.collides_with_entities || e.smart_step || has_agent_collision(*cp, e);
+            });
+            if (i < 0)
+                break;
             if (has_agent_collision(c, c.ents[i]))
                 G::handle_agent_collision(c, i);
             if (c.ents[i].collides_with_entities) {
-                for (int j = h.n_ents - 1; j >= 0; j--) {
-                    if (i == j)
-                        continue;
-                    if (has_collision(c.ents[i], c.ents[j], c.ents[i].collision_margin) && !c.ents[i].will_erase && !c.ents[j].will_erase)
-                        G::handle_collision(c, i, j);
+                int j = h.n_ents;
+                while (true) {
+                    j = pg_scan_down(j, [&](int k) {
+                        const Entity &a = cp->ents[i];
+                        const Entity &b = cp->ents[k];
+                        return k != i && has_collision(a, b, a.collision_margin) && !a.will_erase && !b.will_erase;
+                    });
+                    if (j < 0)
+                        break;
+                    G::handle_collision(c, i, j);
                 }
             }
             if (c.ents[i].smart_step)
@@ -594,6 +617,7 @@ struct Engine {
     static PG_HD void basic_game_reset(Ctx &c) {
         EnvHdr &h = *c.h;
         G::choose_world_dim(c);
+        ctx_refresh(c);
         h.bg_pct_x = rand_rand01(*c.rng);
         h.grid_size = h.main_width * h.main_height;
         if (h.grid_size > c.grid_cap) {
@@ -601,6 +625,7 @@ struct Engine {
             h.main_width = 1;
             h.main_height = 1;
             h.grid_size = 1;
+            ctx_refresh(c);
         }
         h.background_index = rand_randn(*c.rng, c.assets->num_backgrounds);
         h.n_ents = 0;
@@ -733,7 +758,7 @@ struct Defaults {
     static PG_HD bool is_blocked(Ctx &c, int src, int target, bool is_horizontal) {
         if (target == WALL_OBJ)
             return true;
-        if (target == c.h->out_of_bounds_object)
+        if (target == c.oob)
             return true;
         return false;
     }

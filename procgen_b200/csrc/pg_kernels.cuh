@@ -51,6 +51,7 @@ PG_HD Ctx make_ctx(const KParams &p, int env) {
     c.ent_cap = p.ent_stride - 1;
     c.grid_cap = p.grid_stride;
     c.scratch_cap = p.scratch_stride;
+    ctx_refresh(c);
     return c;
 }
 
@@ -66,9 +67,10 @@ PG_HD void write_step_outputs(const KParams &p, int env, const EnvHdr &h) {
 // Construction + first reset (VecGame ctor per-env part vecgame.cpp:309-330, then
 // set_buffers -> reset(); observe(), vecgame.cpp:349-353). One thread.
 template <class G, class Frame>
-PG_HD void env_init_logic(const KParams &p, int env, Frame &f) {
+PG_HD void env_init_logic(const KParams &p, int env) {
     Ctx c = make_ctx(p, env);
     G::init_constants(c);
+    ctx_refresh(c);
     EnvHdr &h = *c.h;
     h.options = p.options;
     h.game_id = p.game_id;
@@ -79,25 +81,57 @@ PG_HD void env_init_logic(const KParams &p, int env, Frame &f) {
     c.rng->seeded = 0;
     Engine<G>::reset(c);
     h.initial_reset_complete = 1;
-    Raster<G, Frame>::frame_setup(c, f, p.snap != 0);
+    Raster<G, Frame>::prepare_camera(c);
     write_step_outputs(p, env, h);
 }
 
 // Game::step (game.cpp:120-155) up to, not including, the pixel work. One thread.
 template <class G, class Frame>
-PG_HD void env_step_logic(const KParams &p, int env, Frame &f) {
+PG_HD void env_step_logic(const KParams &p, int env) {
     Ctx c = make_ctx(p, env);
     c.h->action = p.action[env];  // vecgame.cpp:388
     Engine<G>::step(c);
-    Raster<G, Frame>::frame_setup(c, f, p.snap != 0);
+    Raster<G, Frame>::prepare_camera(c);
     write_step_outputs(p, env, *c.h);
 }
 
 template <class G, class Frame>
-PG_HD void env_render_build(const KParams &p, int env, Frame &f, int tid, int nthreads) {
+PG_HD void env_render_begin(const KParams &p, int env, Frame &f, int tid, int nthreads) {
     Ctx c = make_ctx(p, env);
-    Raster<G, Frame>::frame_build(c, f, tid, nthreads);
+    Raster<G, Frame>::frame_begin(c, f, p.snap != 0, tid, nthreads);
 }
+
+template <class G, class Frame>
+PG_HD void env_render_build(const KParams &p, int env, Frame &f, int tid, int nthreads, int ent_group) {
+    Ctx c = make_ctx(p, env);
+    Raster<G, Frame>::frame_build(c, f, tid, nthreads, ent_group);
+}
+
+template <class G, class Frame>
+PG_HD void env_render_masks(const KParams &p, int env, Frame &f, int tid, int nthreads) {
+    Raster<G, Frame>::frame_masks(f, tid, nthreads);
+}
+
+// R | G<<8 | B<<16 of a 0xAARRGGBB pixel: the byte order of the rgb888 observation (game.cpp:8-23)
+PG_HD uint32_t rgb24_of(uint32_t c) { return ((c >> 16) & 0xffu) | (c & 0xff00u) | ((c & 0xffu) << 16); }
+
+#if defined(__CUDACC__)
+// Device shading loop: thread t shades pixels t, t+T, ...; four neighbouring lanes hold one RGB
+// quad (12 bytes = 3 words), each of the first three lanes assembles one word from its own colour
+// and its right neighbour's (one shuffle) and stores it: every warp store instruction writes 96
+// contiguous bytes of the observation.
+template <class G, class Frame>
+__device__ __forceinline__ void env_render_pixels(const KParams &p, int env, const Frame &f, int tid, int nthreads) {
+    uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3));
+    const int j = tid & 3;
+    for (int pix = tid; pix < RES_W * RES_H; pix += nthreads) {
+        const uint32_t c = rgb24_of(Raster<G, Frame>::shade_pixel(f, pix & (RES_W - 1), pix >> 6, p.atlas));
+        const uint32_t cn = __shfl_down_sync(0xffffffffu, c, 1);
+        if (j != 3)
+            out[(pix >> 2) * 3 + j] = (c >> (8 * j)) | (cn << (24 - 8 * j));
+    }
+}
+#endif
 
 // Shade 4 horizontally adjacent pixels and store them as 12 packed RGB bytes (3 aligned words):
 // bgr32_to_rgb888 (game.cpp:8-23) fused into the shader.
@@ -123,7 +157,7 @@ PG_HD void env_render_quad(const KParams &p, int env, const Frame &f, int quad) 
 // Frame sizing per game: visible window (cells per side) and entity capacity.
 template <class G>
 struct FrameFor {
-    using type = FrameT<G::MAX_VIEW_CELLS, G::ENT_CAP>;
+    using type = FrameT<G::MAX_VIEW_CELLS, G::MAX_VISIBLE_ENTS>;
 };
 
 }  // namespace pg

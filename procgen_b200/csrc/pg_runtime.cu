@@ -109,27 +109,46 @@ std::vector<std::string> split(std::string s, const std::string &delim) {
 }
 
 // ================================================================= kernels
-constexpr int kThreads = 128;
+// Two launches per step:
+//   logic_kernel   one WARP per env. All 32 lanes execute the serial game logic redundantly and in
+//                  lockstep (every load/store is warp-uniform), and fan out only inside
+//                  pg_scan_down, which turns the reference's O(E) entity-collision loops into E/32
+//                  ballots. A warp, not a thread, is the unit so unrelated envs never diverge
+//                  against each other and dozens of envs per SM hide each other's load latency.
+//   render_kernel  one CTA per env: blit-list build + per-pixel gather + packed RGB store
+constexpr int kLogicThreads = 32;                  // one warp = one env = one CTA: a finished env frees
+constexpr int kLogicEnvsPerBlock = kLogicThreads / 32;  // its slot at once (no waiting on CTA siblings)
+constexpr int kRenderThreads = 128;
 constexpr int kQuads = RES_W * RES_H / 4;
 
 #ifndef PG_HOSTSIM
 template <class G, bool INIT>
-__global__ void __launch_bounds__(kThreads) env_kernel(KParams p) {
+__global__ void __launch_bounds__(kLogicThreads) logic_kernel(KParams p) {
+    using Frame = typename FrameFor<G>::type;
+    const int i = (int)blockIdx.x * kLogicEnvsPerBlock + ((int)threadIdx.x >> 5);
+    if (i >= p.env_count)
+        return;
+    const int env = p.env_first + i * p.env_step;
+    if (INIT)
+        env_init_logic<G, Frame>(p, env);
+    else
+        env_step_logic<G, Frame>(p, env);
+}
+
+template <class G>
+__global__ void __launch_bounds__(kRenderThreads) render_kernel(KParams p) {
     using Frame = typename FrameFor<G>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Frame &f = *reinterpret_cast<Frame *>(smem_raw);
     const int env = p.env_first + (int)blockIdx.x * p.env_step;
-    if (threadIdx.x == 0) {
-        if (INIT)
-            env_init_logic<G, Frame>(p, env, f);
-        else
-            env_step_logic<G, Frame>(p, env, f);
-    }
+    const int tid = (int)threadIdx.x;
+    env_render_begin<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
-    env_render_build<G, Frame>(p, env, f, (int)threadIdx.x, (int)blockDim.x);
+    env_render_build<G, Frame>(p, env, f, tid, kRenderThreads, 32);
     __syncthreads();
-    for (int quad = (int)threadIdx.x; quad < kQuads; quad += (int)blockDim.x)
-        env_render_quad<G, Frame>(p, env, f, quad);
+    env_render_masks<G, Frame>(p, env, f, tid, kRenderThreads);
+    __syncthreads();
+    env_render_pixels<G, Frame>(p, env, f, tid, kRenderThreads);
 }
 #endif
 
@@ -148,24 +167,29 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
 #ifndef PG_HOSTSIM
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(env_kernel<G, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Frame)));
+        CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Frame)));
         attr_set = true;
     }
-    env_kernel<G, INIT><<<p.env_count, kThreads, sizeof(Frame), lc.stream>>>(p);
+    const int logic_blocks = (p.env_count + kLogicEnvsPerBlock - 1) / kLogicEnvsPerBlock;
+    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, lc.stream>>>(p);
+    render_kernel<G><<<p.env_count, kRenderThreads, sizeof(Frame), lc.stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
+    (*lc.launch_counter) += 2;
 #else
     static thread_local Frame *f = new Frame;
     for (int b = 0; b < p.env_count; b++) {
         int env = p.env_first + b * p.env_step;
         if (INIT)
-            env_init_logic<G, Frame>(p, env, *f);
+            env_init_logic<G, Frame>(p, env);
         else
-            env_step_logic<G, Frame>(p, env, *f);
-        env_render_build<G, Frame>(p, env, *f, 0, 1);
+            env_step_logic<G, Frame>(p, env);
+        env_render_begin<G, Frame>(p, env, *f, 0, 1);
+        env_render_build<G, Frame>(p, env, *f, 0, 1, 1);
+        env_render_masks<G, Frame>(p, env, *f, 0, 1);
         for (int quad = 0; quad < kQuads; quad++) env_render_quad<G, Frame>(p, env, *f, quad);
     }
+    (*lc.launch_counter) += 2;
 #endif
-    (*lc.launch_counter)++;
 }
 
 struct GameVTable {
@@ -764,7 +788,7 @@ void pgb200_set_stream(libenv_env *handle, void *stream) {
     v->set_device();
     v->sync();
 #ifndef PG_HOSTSIM
-    v->stream = stream ? (cudaStream_t)stream : v->own_stream;
+    v->stream = (stream == PGB200_PRIVATE_STREAM) ? v->own_stream : (cudaStream_t)stream;
 #else
     (void)stream;
 #endif

@@ -156,7 +156,16 @@ struct Ctx {
     int32_t ent_cap;      // list capacity; slot [ent_cap] is the agent ghost slot
     int32_t grid_cap;
     int32_t scratch_cap;  // in int32 words
+    // register-resident copies of header scalars the physics loop reads constantly; refreshed by
+    // ctx_refresh() whenever a game changes them (world size is chosen per episode)
+    int32_t mw, mh, oob;
 };
+
+PG_HD void ctx_refresh(Ctx &c) {
+    c.mw = c.h->main_width;
+    c.mh = c.h->main_height;
+    c.oob = c.h->out_of_bounds_object;
+}
 
 template <class T>
 PG_HD T &game_state(Ctx &c) {
