@@ -28,7 +28,7 @@ CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fno-omit-frame-pointer", "-ffp-contract
 def _compile(src, obj):
     if os.path.exists(obj) and os.path.getmtime(obj) > max(
             os.path.getmtime(src), os.path.getmtime(os.path.join(SHIM, "qt_shim.h")),
-            os.path.getmtime(os.path.join(SHIM, "libenv.h"))):
+            os.path.getmtime(os.path.join(SHIM, "libenv.h")), os.path.getmtime(os.path.join(SHIM, "qt_raster.cpp"))):
         return
     subprocess.check_call(["g++", *CXXFLAGS, "-c", src, "-o", obj])
 
@@ -48,6 +48,8 @@ def build(qt6=False, verbose=False):
     if qt6:
         from oracle import qt6_support  # noqa
         backends.append(("qt6_backend.cpp", "libenv_ref_qt6.so", qt6_support.link_flags()))
+    hook_obj = os.path.join(objdir, "shim_test_hook.o")
+    jobs.append((os.path.join(SHIM, "shim_test_hook.cpp"), hook_obj))
     shim_objs = {}
     for bsrc, _, _ in backends:
         o = os.path.join(objdir, "shim_" + bsrc.replace(".cpp", ".o"))
@@ -59,7 +61,7 @@ def build(qt6=False, verbose=False):
     outs = []
     for bsrc, libname, extra in backends:
         lib = os.path.join(OUT, libname)
-        subprocess.check_call(["g++", "-shared", "-o", lib, *ref_objs, shim_objs[bsrc], "-lz", "-lpthread", *extra])
+        subprocess.check_call(["g++", "-shared", "-o", lib, *ref_objs, shim_objs[bsrc], hook_obj, "-lz", "-lpthread", *extra])
         outs.append(lib)
         if verbose:
             print("built", lib)

@@ -83,7 +83,13 @@ class RefVecEnv:
         lib_path = lib_path or REF_LIB
         if not os.path.exists(lib_path):
             raise FileNotFoundError(f"{lib_path} missing — run python oracle/build_ref.py in the build container")
-        self.lib = C.CDLL(lib_path)
+        if os.path.basename(lib_path) == os.path.basename(REF_LIB_QT6):
+            # real-Qt backend: satisfy Qt's unused DT_NEEDED entries with the empty stub libraries
+            from oracle import qt6_support
+
+            self.lib = C.CDLL(lib_path, handle=qt6_support.lazy_dlopen(lib_path))
+        else:
+            self.lib = C.CDLL(lib_path)
         L = self.lib
         L.libenv_make.restype = C.c_void_p
         L.libenv_make.argtypes = [C.c_int, Options]

@@ -203,6 +203,7 @@ QImage QImage::mirrored(bool horizontal, bool vertical) const {
     return out;
 }
 
+#ifndef QT_SHIM_QT6_BACKEND
 // ---------------------------------------------------------------- QPainter
 
 struct Xform {
@@ -354,24 +355,40 @@ static void draw_scaled(QImage *dev, const QImage &img, QRectF tr, int int_opaci
     }
     if (tr.width() <= 0 || tr.height() <= 0)
         return;
-    const double sx = tr.width() / double(sw);
-    const double sy = tr.height() / double(sh);
-    const int ix = int(0x00010000 / sx);
-    const int iy = int(0x00010000 / sy);
-
-    int tx1 = qRound(tr.x()), ty1 = qRound(tr.y());
-    int tx2 = qRound(tr.x() + tr.width()), ty2 = qRound(tr.y() + tr.height());
+    int ix, iy, dstx, dsty;
+    int tx1, ty1, tx2, ty2, h, w;
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("QT_SHIM_SCALE_VARIANT");
+        variant = e ? atoi(e) : 1;
+    }
+    tx1 = qRound(tr.x()), ty1 = qRound(tr.y());
+    tx2 = qRound(tr.x() + tr.width()), ty2 = qRound(tr.y() + tr.height());
     tx1 = std::max(tx1, 0);
     ty1 = std::max(ty1, 0);
     tx2 = std::min(tx2, dev->w);
     ty2 = std::min(ty2, dev->h);
     if (tx2 <= tx1 || ty2 <= ty1)
         return;
-    int h = ty2 - ty1;
-    int w = tx2 - tx1;
-
-    const int dstx = int(ceil((tx1 + 0.5 - tr.x()) * ix)) - 1;
-    const int dsty = int(ceil((ty1 + 0.5 - tr.y()) * iy)) - 1;
+    h = ty2 - ty1;
+    w = tx2 - tx1;
+    if (variant == 0) {
+        // Qt <= 5.x as recalled in SURVEY: step from the target/source ratio, start from the step
+        const double sx = tr.width() / double(sw);
+        const double sy = tr.height() / double(sh);
+        ix = int(0x00010000 / sx);
+        iy = int(0x00010000 / sy);
+        dstx = int(ceil((tx1 + 0.5 - tr.x()) * ix)) - 1;
+        dsty = int(ceil((ty1 + 0.5 - tr.y()) * iy)) - 1;
+    } else {
+        // Qt 6.6.3 (verified): step and start both from the source/target ratio in double
+        const double sx = double(sw) / tr.width();
+        const double sy = double(sh) / tr.height();
+        ix = int(0x00010000 * sx);
+        iy = int(0x00010000 * sy);
+        dstx = int(ceil((tx1 + 0.5 - tr.x()) * sx * 65536)) - 1;
+        dsty = int(ceil((ty1 + 0.5 - tr.y()) * sy * 65536)) - 1;
+    }
     uint32_t basex = uint32_t(dstx);
     uint32_t srcy = uint32_t(dsty);
 
@@ -515,3 +532,5 @@ void QPainter::drawLine(qreal x1, qreal y1, qreal x2, qreal y2) {
                 blend_px(&px[y * dev->stride + x], pm, io);
         }
 }
+
+#endif  // QT_SHIM_QT6_BACKEND

@@ -28,6 +28,18 @@
 #include <string>
 #include <vector>
 
+// The stand-in classes are renamed at the preprocessor level so their mangled symbols can never
+// collide with (or interpose) the real Qt symbols when the Qt 6 backend links libQt6Gui.
+#define QString pgshim_QString
+#define QPointF pgshim_QPointF
+#define QRect pgshim_QRect
+#define QRectF pgshim_QRectF
+#define QColor pgshim_QColor
+#define QBrush pgshim_QBrush
+#define QPen pgshim_QPen
+#define QImage pgshim_QImage
+#define QPainter pgshim_QPainter
+
 typedef unsigned char uchar;
 typedef double qreal;
 

@@ -43,6 +43,14 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[0] = {"misc_assets/fishTile_072.png"};
         T[2] = {"misc_assets/fishTile_074.png", "misc_assets/fishTile_078.png", "misc_assets/fishTile_080.png"};
         break;
+    case GAME_HEIST:  // heist.cpp:36-60
+        g.bg_group = "topdown_backgrounds";
+        T[51] = {"kenney/Ground/Dirt/dirtCenter.png"};
+        T[9] = {"misc_assets/gemYellow.png"};
+        T[0] = {"misc_assets/spaceAstronauts_008.png"};
+        T[2] = {"misc_assets/keyBlue.png", "misc_assets/keyGreen.png", "misc_assets/keyRed.png"};
+        T[1] = {"misc_assets/lock_blue.png", "misc_assets/lock_green.png", "misc_assets/lock_red.png"};
+        break;
     case GAME_MAZE:  // maze.cpp:26-38
         g.bg_group = "topdown_backgrounds";
         T[51] = {"kenney/Ground/Sand/sandCenter.png"};

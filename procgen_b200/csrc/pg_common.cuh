@@ -145,6 +145,40 @@ PG_HD int pg_scan_down(int upper, F pred) {
 #endif
 }
 
+// pg_warp_for(n, f): f(i) for every i in [0, n); iterations must be independent (disjoint writes).
+// On the device the warp's lanes stride over i and a __syncwarp() publishes the writes before the
+// lanes go back to uniform execution.
+template <class F>
+PG_HD void pg_warp_for(int n, F f) {
+#if defined(__CUDA_ARCH__)
+    for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) f(i);
+    __syncwarp();
+#else
+    for (int i = 0; i < n; i++) f(i);
+#endif
+}
+
+// a[from .. n-2] = a[from+1 .. n-1] for records of `words` int32 each (vector::erase of one element)
+PG_HD void pg_warp_erase(int32_t *a, int from, int n, int words) {
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31u);
+    const int total = (n - 1 - from) * words;
+    int32_t *dst = a + from * words;
+    for (int base = 0; base < total; base += 32) {
+        const int k = base + lane;
+        int32_t v = 0;
+        if (k < total)
+            v = dst[k + words];
+        __syncwarp();
+        if (k < total)
+            dst[k] = v;
+        __syncwarp();
+    }
+#else
+    for (int k = from * words; k < (n - 1) * words; k++) a[k] = a[k + words];
+#endif
+}
+
 // error bits latched per env (the reference would fassert/exit; we must not kill the GPU)
 enum ErrBits : uint32_t {
     ERR_ENTITY_OVERFLOW = 1u << 0,

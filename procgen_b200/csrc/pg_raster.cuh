@@ -97,10 +97,11 @@ PG_HD void make_image_blit(Blit &b, double tx, double ty, double tw, double th, 
     }
     if (!(tw > 0) || !(th > 0))
         return;
-    const double sx = tw / (double)sw;
-    const double sy = th / (double)sh;
-    const int ix = (int)(65536.0 / sx);
-    const int iy = (int)(65536.0 / sy);
+    // Qt 6.6.3 qt_scale_image_32bit: step and start both come from the source/target ratio in double
+    const double sx = (double)sw / tw;
+    const double sy = (double)sh / th;
+    const int ix = (int)(65536.0 * sx);
+    const int iy = (int)(65536.0 * sy);
     int tx1 = pg_qround(tx), ty1 = pg_qround(ty);
     int tx2 = pg_qround(tx + tw), ty2 = pg_qround(ty + th);
     if (tx1 < 0) tx1 = 0;
@@ -111,8 +112,8 @@ PG_HD void make_image_blit(Blit &b, double tx, double ty, double tw, double th, 
         return;
     int h = ty2 - ty1;
     int w = tx2 - tx1;
-    const int dstx = (int)pg_dceil((tx1 + 0.5 - tx) * ix) - 1;
-    const int dsty = (int)pg_dceil((ty1 + 0.5 - ty) * iy) - 1;
+    const int dstx = (int)pg_dceil((tx1 + 0.5 - tx) * sx * 65536) - 1;
+    const int dsty = (int)pg_dceil((ty1 + 0.5 - ty) * sy * 65536) - 1;
     const uint32_t basex = (uint32_t)dstx;
     const uint32_t srcy = (uint32_t)dsty;
     int yend = ((int)(srcy + (uint32_t)iy * (uint32_t)(h - 1))) >> 16;

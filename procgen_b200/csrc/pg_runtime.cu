@@ -21,7 +21,10 @@
 #include "../../include/procgen_b200.h"
 #include "pg_asset_tables.h"
 #include "pg_kernels.cuh"
+#include "games/bigfish.cuh"
 #include "games/coinrun.cuh"
+#include "games/heist.cuh"
+#include "games/maze.cuh"
 
 #ifndef PG_HOSTSIM
 #include <cuda_runtime.h>
@@ -207,7 +210,10 @@ GameVTable make_vtable(int id) {
 
 const GameVTable *find_game(const std::string &name) {
     static const GameVTable table[] = {
+        make_vtable<BigFish>(GAME_BIGFISH),
         make_vtable<CoinRun>(GAME_COINRUN),
+        make_vtable<HeistGame>(GAME_HEIST),
+        make_vtable<MazeGame>(GAME_MAZE),
     };
     for (const auto &g : table)
         if (name == g.name)
