@@ -414,66 +414,357 @@ static void draw_scaled(QImage *dev, const QImage &img, QRectF tr, int int_opaci
     }
 }
 
-// Rotated blit: device pixel covered iff its centre maps inside the target rect; texel chosen by
-// 16.16 fixed-point stepping of the inverse transform along the scanline (fetchTransformed).
+// ---------------------------------------------------------------- transformed (rotated) blits
+// Qt raster engine, non-antialiased, non-smooth drawImage under a rotating world matrix
+// (QRasterPaintEngine::drawImage). Two code paths, both restated:
+//  (T) device bounding box >= 16x16: qt_transform_image (qblendfunctions_p.h): the quad is cut into
+//      three trapezoids whose left/right edges are stepped in 16.16 fixed point; texel coordinates
+//      are an absolute affine function of the device pixel in 16.16.
+//  (R) smaller targets: QRasterizer::rasterizeLine (qrasterizer.cpp) produces spans for the
+//      rotated rectangle (edges stepped in 16.16 from pixel-centre intersections), and
+//      fetchTransformed (qdrawhelper.cpp) walks each span in 16.16 from the inverse matrix of
+//      (translate(1/65536, 1/65536) * image-to-device).
+struct TVertex {
+    double x, y, u, v;
+};
+
+static inline int qFloorI(double v) { return int(floor(v)); }
+static inline int qCeilI(double v) { return int(ceil(v)); }
+
+static void transform_image_rasterize(QImage *dev, const QImage &img, const TVertex &topLeft, const TVertex &bottomLeft,
+                                      const TVertex &topRight, const TVertex &bottomRight, double topY, double bottomY, int dudx,
+                                      int dvdx, int dudy, int dvdy, int u0, int v0, int int_opacity) {
+    const int sw = img.width(), sh = img.height();
+    long long fromY = std::max((long long)qRound(topY), 0LL);
+    long long toY = std::min((long long)qRound(bottomY), (long long)dev->h);
+    if (fromY >= toY)
+        return;
+    double leftSlope = (bottomLeft.x - topLeft.x) / (bottomLeft.y - topLeft.y);
+    double rightSlope = (bottomRight.x - topRight.x) / (bottomRight.y - topRight.y);
+    long long dx_l = (long long)(leftSlope * 0x10000);
+    long long dx_r = (long long)(rightSlope * 0x10000);
+    long long x_l = (long long)((topLeft.x + (0.5 + fromY - topLeft.y) * leftSlope + 0.5) * 0x10000);
+    long long x_r = (long long)((topRight.x + (0.5 + fromY - topRight.y) * rightSlope + 0.5) * 0x10000);
+    const uint32_t *src = img.pixels();
+    uint32_t *px = dev->pixels();
+    for (long long y = fromY; y < toY; ++y) {
+        long long fromX = std::max(x_l >> 16, 0LL);
+        long long toX = std::min(x_r >> 16, (long long)dev->w);
+        if (fromX < toX) {
+            long long u = fromX * dudx + y * dudy + u0;
+            long long v = fromX * dvdx + y * dvdy + v0;
+            for (long long x = fromX; x < toX; ++x) {
+                long long uu = u >> 16, vv = v >> 16;
+                // "Because of rounding, we can get source coordinates outside the source image": clamp
+                uu = std::min(std::max(uu, 0LL), (long long)sw - 1);
+                vv = std::min(std::max(vv, 0LL), (long long)sh - 1);
+                blend_px(&px[y * dev->stride + x], src[vv * img.stride_px() + uu], int_opacity);
+                u += dudx;
+                v += dvdx;
+            }
+        }
+        x_l += dx_l;
+        x_r += dx_r;
+    }
+}
+
+static void draw_transform_image(QImage *dev, const QImage &img, const QRectF &r, const Xform &m, int int_opacity) {
+    const int sw = img.width(), sh = img.height();
+    TVertex v[4];  // TopLeft, TopRight, BottomRight, BottomLeft
+    v[0].u = v[3].u = 0;
+    v[0].v = v[1].v = 0;
+    v[1].u = v[2].u = sw;
+    v[3].v = v[2].v = sh;
+    v[0].x = v[3].x = r.x();
+    v[0].y = v[1].y = r.y();
+    v[1].x = v[2].x = r.x() + r.width();
+    v[3].y = v[2].y = r.y() + r.height();
+    for (int i = 0; i < 4; i++) {
+        double fx = v[i].x, fy = v[i].y;
+        v[i].x = m.m11 * fx + m.m21 * fy + m.dx;
+        v[i].y = m.m12 * fx + m.m22 * fy + m.dy;
+    }
+    int topmost = 0;
+    for (int i = 1; i < 4; ++i)
+        if (v[i].y < v[topmost].y)
+            topmost = i;
+    switch (topmost) {
+    case 1: {
+        TVertex t = v[0];
+        for (int i = 0; i < 3; ++i) v[i] = v[i + 1];
+        v[3] = t;
+    } break;
+    case 2:
+        std::swap(v[0], v[2]);
+        std::swap(v[1], v[3]);
+        break;
+    case 3: {
+        TVertex t = v[3];
+        for (int i = 3; i > 0; --i) v[i] = v[i - 1];
+        v[0] = t;
+    } break;
+    }
+    // if necessary, swap vertex 1 and 3 such that 1 is to the left of 3
+    double dx1 = v[1].x - v[0].x, dy1 = v[1].y - v[0].y;
+    double dx2 = v[3].x - v[0].x, dy2 = v[3].y - v[0].y;
+    if (dx1 * dy2 - dx2 * dy1 > 0)
+        std::swap(v[1], v[3]);
+
+    TVertex u = {v[1].x - v[0].x, v[1].y - v[0].y, v[1].u - v[0].u, v[1].v - v[0].v};
+    TVertex w = {v[2].x - v[0].x, v[2].y - v[0].y, v[2].u - v[0].u, v[2].v - v[0].v};
+    double det = u.x * w.y - u.y * w.x;
+    if (det == 0)
+        return;
+    double invDet = 1.0 / det;
+    double m11 = (u.u * w.y - u.y * w.u) * invDet;
+    double m12 = (u.x * w.u - u.u * w.x) * invDet;
+    double m21 = (u.v * w.y - u.y * w.v) * invDet;
+    double m22 = (u.x * w.v - u.v * w.x) * invDet;
+    double mdx = v[0].u - m11 * v[0].x - m12 * v[0].y;
+    double mdy = v[0].v - m21 * v[0].x - m22 * v[0].y;
+    int dudx = int(m11 * 0x10000);
+    int dvdx = int(m21 * 0x10000);
+    int dudy = int(m12 * 0x10000);
+    int dvdy = int(m22 * 0x10000);
+    int u0 = qCeilI((0.5 * m11 + 0.5 * m12 + mdx) * 0x10000) - 1;
+    int v0 = qCeilI((0.5 * m21 + 0.5 * m22 + mdy) * 0x10000) - 1;
+    if (v[1].y < v[3].y) {
+        transform_image_rasterize(dev, img, v[0], v[1], v[0], v[3], v[0].y, v[1].y, dudx, dvdx, dudy, dvdy, u0, v0, int_opacity);
+        transform_image_rasterize(dev, img, v[1], v[2], v[0], v[3], v[1].y, v[3].y, dudx, dvdx, dudy, dvdy, u0, v0, int_opacity);
+        transform_image_rasterize(dev, img, v[1], v[2], v[3], v[2], v[3].y, v[2].y, dudx, dvdx, dudy, dvdy, u0, v0, int_opacity);
+    } else {
+        transform_image_rasterize(dev, img, v[0], v[1], v[0], v[3], v[0].y, v[3].y, dudx, dvdx, dudy, dvdy, u0, v0, int_opacity);
+        transform_image_rasterize(dev, img, v[0], v[1], v[3], v[2], v[3].y, v[1].y, dudx, dvdx, dudy, dvdy, u0, v0, int_opacity);
+        transform_image_rasterize(dev, img, v[1], v[2], v[3], v[2], v[1].y, v[2].y, dudx, dvdx, dudy, dvdy, u0, v0, int_opacity);
+    }
+}
+
+// ---- path (R): spans from QRasterizer::rasterizeLine, texels from fetchTransformed
+struct SpanSink {
+    QImage *dev;
+    const QImage *img;
+    int io;
+    // inverse of (translate(1/65536,1/65536) * image->device)
+    double m11, m12, m21, m22, dx, dy;
+    void span(int x, int len, int y) const {
+        if (y < 0 || y >= dev->h)
+            return;
+        if (x < 0) {
+            len += x;
+            x = 0;
+        }
+        if (x + len > dev->w)
+            len = dev->w - x;
+        if (len <= 0)
+            return;
+        const int sw = img->width(), sh = img->height();
+        const double fixed_scale = 65536.0;
+        const double cx = x + 0.5, cy = y + 0.5;
+        const int fdx = int(m11 * fixed_scale);
+        const int fdy = int(m12 * fixed_scale);
+        int fx = int((m21 * cy + m11 * cx + dx) * fixed_scale);
+        int fy = int((m22 * cy + m12 * cx + dy) * fixed_scale);
+        const uint32_t *src = img->pixels();
+        uint32_t *px = dev->pixels();
+        for (int i = 0; i < len; i++) {
+            int tx = std::min(std::max(fx >> 16, 0), sw - 1);
+            int ty = std::min(std::max(fy >> 16, 0), sh - 1);
+            blend_px(&px[y * dev->stride + x + i], src[ty * img->stride_px() + tx], io);
+            fx += fdx;
+            fy += fdy;
+        }
+    }
+};
+
+static inline bool q26Dot6Compare(double p1, double p2) { return int((p2 - p1) * 64.) == 0; }
+static inline double qSafeDivide(double x, double y) {
+    if (y == 0)
+        return x > 0 ? 1e20 : -1e20;
+    return x / y;
+}
+static inline int qSafeFloatToQ16Dot16(double x) {
+    double tmp = x * 65536.;
+    if (tmp > double(INT32_MAX))
+        return INT32_MAX;
+    if (tmp < -double(INT32_MAX))
+        return -INT32_MAX;
+    return int(tmp);
+}
+static inline int FloatToQ16Dot16(double i) { return int(i * 65536.); }
+static inline double qBoundD(double lo, double v, double hi) { return std::max(lo, std::min(hi, v)); }
+
+// QRasterizer::rasterizeLine(a, b, width), non-antialiased, clip = device rect
+static void rasterize_line(const SpanSink &sink, double ax, double ay, double bx, double by, double width) {
+    const int clipL = 0, clipT = 0, clipR = sink.dev->w - 1, clipB = sink.dev->h - 1;  // inclusive QRect edges
+    if ((ax == bx && ay == by) || width == 0)
+        return;
+    double pax = ax, pay = ay, pbx = bx, pby = by;
+    {
+        static double off = -1e9;
+        if (off < -1e8) {
+            const char *e = getenv("QT_SHIM_LINE_OFFSET");
+            off = e ? atof(e) : 0.0;
+        }
+        pax += off; pay += off; pbx += off; pby += off;
+    }
+    // (clipping of far-away endpoints is skipped: sprites are at most a few device pixels off screen)
+    if (q26Dot6Compare(pay, pby)) {
+        const double x = (pax + pbx) * 0.5f;
+        const double dx = fabs(pbx - pax) * 0.5f;
+        const double y = pay;
+        const double dy = width * dx;
+        pax = x;
+        pay = y - dy;
+        pbx = x;
+        pby = y + dy;
+        width = 1 / width;
+    }
+    if (q26Dot6Compare(pax, pbx)) {
+        if (pay > pby) {
+            std::swap(pax, pbx);
+            std::swap(pay, pby);
+        }
+        const double dy = pby - pay;
+        const double halfWidth = 0.5f * width * dy;
+        double left = pax - halfWidth;
+        double right = pax + halfWidth;
+        left = qBoundD(double(clipL), left, double(clipR + 1));
+        right = qBoundD(double(clipL), right, double(clipR + 1));
+        pay = qBoundD(double(clipT), pay, double(clipB + 1));
+        pby = qBoundD(double(clipT), pby, double(clipB + 1));
+        if (q26Dot6Compare(left, right) || q26Dot6Compare(pay, pby))
+            return;
+        int iTop = int(pay + 0.5f);
+        int iBottom = pby < 0.5f ? -1 : int(pby - 0.5f);
+        int iLeft = int(left + 0.5f);
+        int iRight = right < 0.5f ? -1 : int(right - 0.5f);
+        int iWidth = iRight - iLeft + 1;
+        for (int y = iTop; y <= iBottom; ++y) sink.span(iLeft, iWidth, y);
+        return;
+    }
+    if (pay > pby) {
+        std::swap(pax, pbx);
+        std::swap(pay, pby);
+    }
+    double deltax = (pbx - pax) * (0.5f * width), deltay = (pby - pay) * (0.5f * width);
+    const double perpx = deltay, perpy = -deltax;
+    double topx, topy, leftx, lefty, rightx, righty, bottomx, bottomy;
+    if (pax < pbx) {
+        topx = pax + perpx; topy = pay + perpy;
+        leftx = pax - perpx; lefty = pay - perpy;
+        rightx = pbx + perpx; righty = pby + perpy;
+        bottomx = pbx - perpx; bottomy = pby - perpy;
+    } else {
+        topx = pax - perpx; topy = pay - perpy;
+        leftx = pbx - perpx; lefty = pby - perpy;
+        rightx = pax + perpx; righty = pay + perpy;
+        bottomx = pbx + perpx; bottomy = pby + perpy;
+    }
+    const double topLeftSlope = qSafeDivide(leftx - topx, lefty - topy);
+    const double bottomLeftSlope = qSafeDivide(bottomx - leftx, bottomy - lefty);
+    const double topRightSlope = qSafeDivide(rightx - topx, righty - topy);
+    const double bottomRightSlope = qSafeDivide(bottomx - rightx, bottomy - righty);
+    const int topLeftSlopeFP = qSafeFloatToQ16Dot16(topLeftSlope);
+    const int topRightSlopeFP = qSafeFloatToQ16Dot16(topRightSlope);
+    const int bottomLeftSlopeFP = qSafeFloatToQ16Dot16(bottomLeftSlope);
+    const int bottomRightSlopeFP = qSafeFloatToQ16Dot16(bottomRightSlope);
+
+    static double oT = 0, oB = 0, oL = 0, oR = 0, oS = 0;
+    static bool init = false;
+    if (!init) {
+        init = true;
+        const char *e = getenv("QT_SHIM_EDGE_OFFSETS");
+        if (e) sscanf(e, "%lf,%lf,%lf,%lf,%lf", &oT, &oB, &oL, &oR, &oS);
+    }
+    int iTop = int(topy + 0.5f + oT);
+    int iLeft = lefty + oB < 0.5f ? -1 : int(lefty - 0.5f + oB);
+    int iRight = righty + oB < 0.5f ? -1 : int(righty - 0.5f + oB);
+    int iBottom = bottomy + oB < 0.5f ? -1 : int(bottomy - 0.5f + oB);
+    int iMiddle = std::min(iLeft, iRight);
+
+    int leftIntersectAf = FloatToQ16Dot16(topx + 0.5f + oL + (iTop + 0.5f + oS - topy) * topLeftSlope);
+    int leftIntersectBf = FloatToQ16Dot16(leftx + 0.5f + oL + (iLeft + 1.5f + oS - lefty) * bottomLeftSlope);
+    int rightIntersectAf = FloatToQ16Dot16(topx - 0.5f + oR + (iTop + 0.5f + oS - topy) * topRightSlope);
+    int rightIntersectBf = FloatToQ16Dot16(rightx - 0.5f + oR + (iRight + 1.5f + oS - righty) * bottomRightSlope);
+
+    int y = iTop;
+    auto segment = [&](int next, int &li, int &ri, int ls, int rs) {
+        int ny = std::min(next + 1, clipT);
+        if (y < ny) {
+            li += ls * (ny - y);
+            ri += rs * (ny - y);
+            y = ny;
+        }
+        if (next > clipB)
+            next = clipB;
+        for (; y <= next; ++y) {
+            const int x1 = std::max(li >> 16, clipL);
+            const int x2 = std::min(ri >> 16, clipR);
+            if (x2 >= x1)
+                sink.span(x1, x2 - x1 + 1, y);
+            li += ls;
+            ri += rs;
+        }
+    };
+    segment(iMiddle, leftIntersectAf, rightIntersectAf, topLeftSlopeFP, topRightSlopeFP);
+    segment(iRight, leftIntersectBf, rightIntersectAf, bottomLeftSlopeFP, topRightSlopeFP);
+    segment(iLeft, leftIntersectAf, rightIntersectBf, topLeftSlopeFP, bottomRightSlopeFP);
+    segment(iBottom, leftIntersectBf, rightIntersectBf, bottomLeftSlopeFP, bottomRightSlopeFP);
+}
+
 static void draw_rotated(QImage *dev, const QImage &img, const QRectF &r, const Xform &m, int int_opacity) {
     const int sw = img.width(), sh = img.height();
     if (sw <= 0 || sh <= 0 || r.width() <= 0 || r.height() <= 0)
         return;
-    // image->device: scale(r.w/sw, r.h/sh) then translate(r.x, r.y) then m
-    const double sx = r.width() / sw, sy = r.height() / sh;
-    double a11 = m.m11 * sx, a12 = m.m12 * sx;
-    double a21 = m.m21 * sy, a22 = m.m22 * sy;
-    double adx = m.dx + r.x() * m.m11 + r.y() * m.m21;
-    double ady = m.dy + r.x() * m.m12 + r.y() * m.m22;
-    double det = a11 * a22 - a12 * a21;
-    if (det == 0)
-        return;
-    double i11 = a22 / det, i12 = -a12 / det, i21 = -a21 / det, i22 = a11 / det;
-    double idx = -(adx * i11 + ady * i21), idy = -(adx * i12 + ady * i22);
-    // device-space bounding box of the rect corners
-    double minx = 1e30, miny = 1e30, maxx = -1e30, maxy = -1e30;
+    // targetBounds = s->matrix.mapRect(r): bounding box of the four mapped corners
+    double minx = 1e300, miny = 1e300, maxx = -1e300, maxy = -1e300;
     for (int c = 0; c < 4; c++) {
-        double u = (c & 1) ? sw : 0, v = (c & 2) ? sh : 0;
-        double X = a11 * u + a21 * v + adx, Y = a12 * u + a22 * v + ady;
+        double fx = (c & 1) ? r.x() + r.width() : r.x(), fy = (c & 2) ? r.y() + r.height() : r.y();
+        double X = m.m11 * fx + m.m21 * fy + m.dx, Y = m.m12 * fx + m.m22 * fy + m.dy;
         minx = std::min(minx, X);
         maxx = std::max(maxx, X);
         miny = std::min(miny, Y);
         maxy = std::max(maxy, Y);
     }
-    int x0 = std::max(0, int(floor(minx)) - 1), x1 = std::min(dev->w - 1, int(ceil(maxx)) + 1);
-    int y0 = std::max(0, int(floor(miny)) - 1), y1 = std::min(dev->h - 1, int(ceil(maxy)) + 1);
-    const uint32_t *src = img.pixels();
-    uint32_t *px = dev->pixels();
-    const double fixed_scale = 65536.0;
-    const int fdx = int(i11 * fixed_scale), fdy = int(i12 * fixed_scale);
-    for (int y = y0; y <= y1; y++) {
-        bool started = false;
-        int fx = 0, fy = 0;
-        for (int x = x0; x <= x1; x++) {
-            const double cx = x + 0.5, cy = y + 0.5;
-            double u = i11 * cx + i21 * cy + idx;
-            double v = i12 * cx + i22 * cy + idy;
-            bool inside = (u >= 0 && u < sw && v >= 0 && v < sh);
-            if (!inside) {
-                if (started) {
-                    fx += fdx;
-                    fy += fdy;
-                }
-                continue;
-            }
-            if (!started) {
-                fx = int(u * fixed_scale);
-                fy = int(v * fixed_scale);
-                started = true;
-            }
-            int tx = std::min(std::max(fx >> 16, 0), sw - 1);
-            int ty = std::min(std::max(fy >> 16, 0), sh - 1);
-            blend_px(&px[y * dev->stride + x], src[ty * img.stride_px() + tx], int_opacity);
-            fx += fdx;
-            fy += fdy;
-        }
+    if (maxx - minx >= 16 && maxy - miny >= 16) {
+        draw_transform_image(dev, img, r, m, int_opacity);
+        return;
     }
+    // copy = matrix; copy.translate(r.x, r.y); copy.scale(r.w / sw, r.h / sh)
+    double c11 = m.m11, c12 = m.m12, c21 = m.m21, c22 = m.m22;
+    double cdx = m.dx + r.x() * m.m11 + r.y() * m.m21;
+    double cdy = m.dy + r.y() * m.m22 + r.x() * m.m12;
+    const double sx = r.width() / double(sw), sy = r.height() / double(sh);
+    c11 *= sx;
+    c12 *= sx;
+    c21 *= sy;
+    c22 *= sy;
+    // QSpanData::setupMatrix: inv = (translate(1/65536, 1/65536) * copy).inverted()
+    const double t = 1.0 / 65536;
+    double pdx = t * c11 + t * c21 + cdx;
+    double pdy = t * c12 + t * c22 + cdy;
+    double det = c11 * c22 - c12 * c21;
+    if (det == 0)
+        return;
+    double dinv = 1.0 / det;
+    SpanSink sink;
+    sink.dev = dev;
+    sink.img = &img;
+    sink.io = int_opacity;
+    sink.m11 = c22 * dinv;
+    sink.m12 = -c12 * dinv;
+    sink.m21 = -c21 * dinv;
+    sink.m22 = c11 * dinv;
+    sink.dx = (c21 * pdy - c22 * pdx) * dinv;
+    sink.dy = (c12 * pdx - c11 * pdy) * dinv;
+    // a, b = matrix.map of the mid points of the left and right edges of r
+    double lx = r.x(), ly = (r.y() + (r.y() + r.height())) * 0.5f;
+    double rx = r.x() + r.width(), ry = ly;
+    lx = (r.x() + r.x()) * 0.5f;
+    rx = ((r.x() + r.width()) + (r.x() + r.width())) * 0.5f;
+    double ax = m.m11 * lx + m.m21 * ly + m.dx, ay = m.m12 * lx + m.m22 * ly + m.dy;
+    double bx = m.m11 * rx + m.m21 * ry + m.dx, by = m.m12 * rx + m.m22 * ry + m.dy;
+    rasterize_line(sink, ax, ay, bx, by, r.height() / r.width());
 }
 
 void QPainter::drawImage(const QRectF &target, const QImage &image) {

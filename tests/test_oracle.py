@@ -65,3 +65,30 @@ def test_oracle_reproduces_golden(ref_lib, asset_pack, fixture):
         assert hashlib.sha256(ob["rgb"].tobytes()).hexdigest() == str(g["rgb_sha256"][t])
     assert np.array_equal(ob["rgb"], g["last_rgb"])
     env.close()
+
+
+def test_raster_restatement_matches_real_qt6(ref_lib, asset_pack):
+    """The CPU raster restatement vs a REAL Qt raster engine (Qt 6.6.3 shipped with Nsight Compute):
+    zero differing pixels for the un-rotated draw paths of coinrun / bigfish / maze."""
+    from oracle import build_ref, qt6_support
+    from oracle.ref_env import REF_LIB_QT6
+
+    if not qt6_support.available():
+        pytest.skip("Qt 6 libraries (Nsight Compute) not present")
+    if not os.path.exists(REF_LIB_QT6):
+        if not build_ref.reference_available():
+            pytest.skip("libenv_ref_qt6.so not built and reference tree absent")
+        build_ref.build(qt6=True)
+    for name, mode in [("coinrun", "hard"), ("bigfish", "hard"), ("maze", "hard")]:
+        n, steps = 8, 150
+        a = RefVecEnv(n, name, distribution_mode=mode, num_levels=0, rand_seed=3)
+        b = RefVecEnv(n, name, distribution_mode=mode, num_levels=0, rand_seed=3, lib_path=REF_LIB_QT6)
+        acts = mt19937_actions(0, n, steps)
+        for t in range(steps):
+            a.act(acts[t])
+            b.act(acts[t])
+            _, oa, _ = a.observe()
+            _, ob, _ = b.observe()
+            assert np.array_equal(oa["rgb"], ob["rgb"]), f"{name} step {t}: restatement != Qt 6.6.3"
+        a.close()
+        b.close()
