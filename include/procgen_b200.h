@@ -164,6 +164,11 @@ LIBENV_API void pgb200_sync(libenv_env *handle);
  * latches a bit instead. Copies num_envs words to `host_out`; returns the OR of all of them. */
 LIBENV_API uint32_t pgb200_get_errors(libenv_env *handle, uint32_t *host_out);
 
+/* Profiling aid: when the environment variable PGB200_DEBUG_TIMING is set at libenv_make time, the
+ * logic kernel records each env's duration of the last step in SM cycles; copies num_envs words.
+ * Returns -1 when timing was not enabled. */
+LIBENV_API int pgb200_debug_cycles(libenv_env *handle, uint32_t *host_out);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 LIBENV_API int64_t pgb200_kernel_launches(libenv_env *handle);
 

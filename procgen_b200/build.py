@@ -34,7 +34,8 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, os.path.join(CSRC, "pg_runtime.cu"), "-o", LIB_PATH, "-lz", "-ldl"]
+    extra = os.environ.get("PG_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, os.path.join(CSRC, "pg_runtime.cu"), "-o", LIB_PATH, "-lz", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -63,6 +63,11 @@ struct CoinRun : Defaults<CoinRun>, DrawDefaults<CoinRun> {
     static PG_HD bool will_reflect(Ctx &c, int src, int target) {
         return (src == ENEMY && (is_wall(target) || target == ENEMY_BARRIER));
     }
+    // is_blocked_ents (:187-203) can only be true for CRATE or a type is_blocked accepts; will_reflect
+    // (:140-142) only for wall-like types. Entity types here: PLAYER, SAW, ENEMY, CRATE, TRAIL.
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int target) {
+        return target == CRATE || target == WALL_OBJ || target == c.oob || is_wall(target) || target == ENEMY_BARRIER;
+    }
     // coinrun.cpp:144-154
     static PG_HD void handle_grid_collision(Ctx &c, int oi, int type, int i, int j) {
         if (c.ents[oi].type == PLAYER) {

@@ -110,7 +110,10 @@ struct HeistGame : Defaults<HeistGame>, DrawDefaults<HeistGame> {
         agent_of(c).y = -1;
         int off_x = rand_randn(rg, world_dim - maze_dim + 1);
         int off_y = rand_randn(rg, world_dim - maze_dim + 1);
-        for (int i = 0; i < h.grid_size; i++) E::set_obj_idx(c, i, WALL_OBJ);
+        {
+            int16_t *g = c.grid;
+            pg_warp_for(h.grid_size, [=](int i) { g[i] = (int16_t)WALL_OBJ; });
+        }
         for (int i = 0; i < maze_dim; i++) {
             for (int j = 0; j < maze_dim; j++) {
                 int x = off_x + i;

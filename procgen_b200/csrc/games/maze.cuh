@@ -64,7 +64,10 @@ struct MazeGame : Defaults<MazeGame>, DrawDefaults<MazeGame> {
         a.y = (float)(margin + .5);
         mg.generate_maze();
         mg.place_objects(GOAL, 1);
-        for (int i = 0; i < h.grid_size; i++) E::set_obj_idx(c, i, WALL_OBJ);
+        {
+            int16_t *g = c.grid;
+            pg_warp_for(h.grid_size, [=](int i) { g[i] = (int16_t)WALL_OBJ; });
+        }
         for (int i = 0; i < mg.maze_dim; i++)
             for (int j = 0; j < mg.maze_dim; j++)
                 E::set_obj(c, margin + i, margin + j, mg.grid_get(i + MAZE_OFFSET, j + MAZE_OFFSET));

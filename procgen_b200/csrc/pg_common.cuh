@@ -145,6 +145,47 @@ PG_HD int pg_scan_down(int upper, F pred) {
 #endif
 }
 
+// Descending scan that keeps the rest of a chunk's ballot when handling a hit changed nothing
+// the predicate depends on (the common case: overlapping but non-interacting entities such as
+// trails); `restart_below(i)` discards it after a hit that moved something.
+struct ScanDownIter {
+    int next_base;   // highest index of the next chunk to test
+    int cur_base;    // highest index of the chunk `mask` belongs to
+    unsigned mask;   // device: remaining hits of the current chunk (bit = lane, lane 0 = cur_base)
+    PG_HD explicit ScanDownIter(int upper) : next_base(upper - 1), cur_base(upper - 1), mask(0) {}
+    template <class F>
+    PG_HD int next(F pred) {
+#if defined(__CUDA_ARCH__)
+        const int lane = (int)(threadIdx.x & 31u);
+        while (true) {
+            if (mask) {
+                const int b = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                return cur_base - b;
+            }
+            if (next_base < 0)
+                return -1;
+            cur_base = next_base;
+            next_base -= 32;
+            const int i = cur_base - lane;
+            const bool hit = (i >= 0) && pred(i);
+            mask = __ballot_sync(0xffffffffu, hit);
+        }
+#else
+        while (next_base >= 0) {
+            const int i = next_base--;
+            if (pred(i))
+                return i;
+        }
+        return -1;
+#endif
+    }
+    PG_HD void restart_below(int i) {
+        mask = 0;
+        next_base = i - 1;
+    }
+};
+
 // pg_warp_for(n, f): f(i) for every i in [0, n); iterations must be independent (disjoint writes).
 // On the device the warp's lanes stride over i and a __syncwarp() publishes the writes before the
 // lanes go back to uniform execution.

@@ -122,12 +122,17 @@ struct Engine {
             return INVALID_IDX;
         return y * c.mw + x;
     }
-    // basic-abstract-game.cpp:125-131 (elem travels through a `char`)
+    // basic-abstract-game.cpp:125-131 (elem travels through a `char`). The cells are independent, so
+    // the warp's lanes split the rectangle (level generation is the long tail of a step).
     static PG_HD void fill_elem(Ctx &c, int x, int y, int dx, int dy, int elem) {
         const int v = (int)(signed char)elem;
-        for (int j = 0; j < dx; j++)
-            for (int k = 0; k < dy; k++)
-                set_obj(c, x + j, y + k, v);
+        if (dx <= 0 || dy <= 0)
+            return;
+        Ctx *cp = &c;
+        pg_warp_for(dx * dy, [=](int k) {
+            const int j = k / dy;
+            set_obj(*cp, x + j, y + (k - j * dy), v);
+        });
     }
     // basic-abstract-game.cpp:167-174 — floor() is the double overload
     static PG_HD int get_obj_from_floats(Ctx &c, float i, float j) {
@@ -389,13 +394,19 @@ struct Engine {
         // reference: for i = n-1..0 { skip self/erased; if (has_collision) {...} } — the test runs
         // warp-wide, the (rare) hits are handled one at a time in descending order, and the scan
         // restarts below each hit because handling may have moved things.
-        int i = c.h->n_ents;
+        ScanDownIter it(c.h->n_ents);
         while (true) {
             const Entity *ents = c.ents;
             const float ox = obj.x, oy = obj.y, orx = obj.rx, ory = obj.ry;  // hoisted: warp-uniform
-            i = pg_scan_down(i, [&](int k) {
+            const int otype = obj.type;
+            Ctx &cp0 = c;
+            const int i = it.next([&](int k) {
                 const Entity &mm = ents[k];
                 if (k == oi || mm.will_erase)
+                    return false;
+                // overlaps that can neither block nor reflect change nothing (:332-356); games may
+                // declare such type pairs so they are dropped inside the warp-wide test
+                if (!G::may_block_or_reflect(cp0, otype, mm.type))
                     return false;
                 // has_collision(obj, m, POS_EPS), basic-abstract-game.cpp:1145-1150
                 float threshold_x = (orx + mm.rx) + POS_EPS;
@@ -406,9 +417,11 @@ struct Engine {
                 break;
             Entity &m = c.ents[i];
             bool curr_block = false;
+            bool moved = false;
             if (G::is_blocked_ents(c, oi, i, is_horizontal)) {
                 curr_block = true;
             } else if (G::will_reflect(c, obj.type, m.type)) {
+                moved = true;
                 if (is_horizontal) {
                     float delx = m.x - obj.x;
                     float rsum = m.rx + obj.rx;
@@ -421,9 +434,14 @@ struct Engine {
                     obj.vy = -1 * obj.vy;
                 }
             }
-            if (curr_block)
+            if (curr_block) {
                 push_obj(c, i, oi, is_horizontal, depth);
+                moved = true;
+            }
             block2 = block2 || curr_block;
+            // positions / erase flags may have changed: the remaining ballot bits are stale
+            if (moved)
+                it.restart_below(i);
         }
         return block || block2;
     }
@@ -644,7 +662,10 @@ struct Engine {
         c.ents[ai].render_z = 1;
         erase_if_needed(c);
         // grid.resize() zero-fills, then fill_elem(..., SPACE)
-        for (int i = 0; i < h.grid_size; i++) c.grid[i] = (int16_t)SPACE;
+        {
+            int16_t *g = c.grid;
+            pg_warp_for(h.grid_size, [=](int i) { g[i] = (int16_t)SPACE; });
+        }
     }
 
     // ---- Game::reset / Game::step (game.cpp:93-155)
@@ -766,6 +787,9 @@ struct Defaults {
         return G::is_blocked(c, src, c.ents[target].type, is_horizontal);
     }
     static PG_HD bool will_reflect(Ctx &c, int src_type, int target_type) { return false; }
+    // PURE, conservative pre-filter for sub_step's entity scan: false only if an overlap between
+    // entities of these two types can never make is_blocked_ents or will_reflect return true.
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src_type, int target_type) { return true; }
     static PG_HD float get_agent_acceleration_scale(Ctx &c) { return 1.0; }
     static PG_HD void handle_agent_collision(Ctx &c, int obj) {}
     static PG_HD void handle_grid_collision(Ctx &c, int obj, int type, int i, int j) {}

@@ -37,6 +37,7 @@ struct KParams {
     int32_t game_id;
     int32_t snap;
     int32_t env_global_offset;  // game_n = env_global_offset + env
+    uint32_t *dbg_cycles;       // optional [N] per-env logic duration in SM cycles (profiling aid)
 };
 
 PG_HD Ctx make_ctx(const KParams &p, int env) {
@@ -85,9 +86,50 @@ PG_HD void env_init_logic(const KParams &p, int env) {
     write_step_outputs(p, env, h);
 }
 
+#if defined(__CUDACC__)
+// Warm the env's working set. A step's logic is one long dependent chain; touched cold, every
+// entity record / header line / grid row costs a serial DRAM round trip. Here the 32 lanes issue
+// all those line fetches at once (prefetch.global.L2 + L1), so the chain later runs on cache hits.
+__device__ __forceinline__ void pg_prefetch_line(const void *ptr) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+__device__ __forceinline__ void env_prefetch(const KParams &p, int env) {
+    const int lane = (int)(threadIdx.x & 31u);
+    const char *hdr = reinterpret_cast<const char *>(p.hdr + env);
+    if (lane < (int)((sizeof(EnvHdr) + 127) / 128))
+        pg_prefetch_line(hdr + lane * 128);
+    const MT19937 *rng = p.rng + env;
+    if (lane == 8)
+        pg_prefetch_line(&rng->p);
+    const Entity *ents = p.ents + (size_t)env * p.ent_stride;
+    const int n = p.hdr[env].n_ents;   // first demand load (same line as the prefetch above)
+    for (int i = lane; i < n; i += 32) pg_prefetch_line(ents + i);
+    // RNG words of the next draw and the grid rows around the agent
+    if (lane == 9) {
+        int k = rng->p >= 624 ? 0 : rng->p;
+        pg_prefetch_line(&rng->mt[k]);
+        pg_prefetch_line(&rng->mt[(k + 397) % 624]);
+    }
+    if (lane >= 16 && lane < 24 && n > 0) {
+        const EnvHdr &h = p.hdr[env];
+        const Entity &a = ents[h.agent_idx];
+        int row = (int)a.y + (lane - 16) - 3;
+        if (row >= 0 && row < h.main_height) {
+            int col = (int)a.x - 4;
+            if (col < 0) col = 0;
+            pg_prefetch_line(p.grid + (size_t)env * p.grid_stride + row * h.main_width + col);
+        }
+    }
+    __syncwarp();
+}
+#endif
+
 // Game::step (game.cpp:120-155) up to, not including, the pixel work. One thread.
 template <class G, class Frame>
 PG_HD void env_step_logic(const KParams &p, int env) {
+#if defined(__CUDA_ARCH__)
+    env_prefetch(p, env);
+#endif
     Ctx c = make_ctx(p, env);
     c.h->action = p.action[env];  // vecgame.cpp:388
     Engine<G>::step(c);

@@ -119,23 +119,48 @@ std::vector<std::string> split(std::string s, const std::string &delim) {
 //                  ballots. A warp, not a thread, is the unit so unrelated envs never diverge
 //                  against each other and dozens of envs per SM hide each other's load latency.
 //   render_kernel  one CTA per env: blit-list build + per-pixel gather + packed RGB store
-constexpr int kLogicThreads = 32;                  // one warp = one env = one CTA: a finished env frees
-constexpr int kLogicEnvsPerBlock = kLogicThreads / 32;  // its slot at once (no waiting on CTA siblings)
+#ifndef PG_LOGIC_WARPS
+#define PG_LOGIC_WARPS 2
+#endif
+#ifndef PG_LOGIC_MIN_BLOCKS
+#define PG_LOGIC_MIN_BLOCKS 24
+#endif
+#ifndef PG_STEP_CHUNKS
+#define PG_STEP_CHUNKS 4
+#endif
+#ifndef PG_AUX_STREAMS
+#define PG_AUX_STREAMS 2
+#endif
+constexpr int kLogicThreads = 32 * PG_LOGIC_WARPS;  // one warp = one env; few warps per CTA so a finished
+constexpr int kLogicEnvsPerBlock = PG_LOGIC_WARPS;  // env frees its slot without waiting on many siblings
 constexpr int kRenderThreads = 128;
 constexpr int kQuads = RES_W * RES_H / 4;
 
 #ifndef PG_HOSTSIM
+// Persistent: the grid is sized to fill the machine once and every warp pulls env indices from a
+// global ticket counter until the launch's range is exhausted, so a long env (level reset) only
+// delays its own warp and no SM slot idles waiting for a block launch.
 template <class G, bool INIT>
-__global__ void __launch_bounds__(kLogicThreads) logic_kernel(KParams p) {
+__global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kernel(KParams p, unsigned int *ticket) {
     using Frame = typename FrameFor<G>::type;
-    const int i = (int)blockIdx.x * kLogicEnvsPerBlock + ((int)threadIdx.x >> 5);
-    if (i >= p.env_count)
-        return;
-    const int env = p.env_first + i * p.env_step;
-    if (INIT)
-        env_init_logic<G, Frame>(p, env);
-    else
-        env_step_logic<G, Frame>(p, env);
+    const unsigned lane = threadIdx.x & 31u;
+    while (true) {
+        unsigned t = 0;
+        if (lane == 0)
+            t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= (unsigned)p.env_count)
+            break;
+        const int env = p.env_first + (int)t * p.env_step;
+        const long long t0 = p.dbg_cycles ? clock64() : 0;
+        if (INIT)
+            env_init_logic<G, Frame>(p, env);
+        else
+            env_step_logic<G, Frame>(p, env);
+        __syncwarp();
+        if (p.dbg_cycles && lane == 0)
+            p.dbg_cycles[env] = (uint32_t)(clock64() - t0);
+    }
 }
 
 template <class G>
@@ -158,6 +183,8 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(KParams p) {
 struct LaunchCtx {
 #ifndef PG_HOSTSIM
     cudaStream_t stream;
+    unsigned int *ticket;     // work counter of this launch slot (one per in-flight logic kernel)
+    int max_logic_blocks;     // SM count x resident CTAs per SM
 #endif
     int64_t *launch_counter;
 };
@@ -173,8 +200,11 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
         CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Frame)));
         attr_set = true;
     }
-    const int logic_blocks = (p.env_count + kLogicEnvsPerBlock - 1) / kLogicEnvsPerBlock;
-    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, lc.stream>>>(p);
+    int logic_blocks = (p.env_count + kLogicEnvsPerBlock - 1) / kLogicEnvsPerBlock;
+    if (logic_blocks > lc.max_logic_blocks)
+        logic_blocks = lc.max_logic_blocks;
+    CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, sizeof(unsigned int), lc.stream));
+    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, lc.stream>>>(p, lc.ticket);
     render_kernel<G><<<p.env_count, kRenderThreads, sizeof(Frame), lc.stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
     (*lc.launch_counter) += 2;
@@ -270,7 +300,15 @@ struct VecEnv {
 #ifndef PG_HOSTSIM
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    static constexpr int kAuxStreams = PG_AUX_STREAMS;
+    cudaStream_t aux[kAuxStreams] = {};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[kAuxStreams] = {};
 #endif
+    static constexpr int kChunks = PG_STEP_CHUNKS;
+    static constexpr int kMaxTickets = 64;
+    unsigned int *d_tickets = nullptr;
+    int max_logic_blocks = 1 << 30;
     // host-buffer (libenv) mode
     bool have_host_bufs = false;
     bool ob_direct = false;      // caller's obs block is contiguous and page-locked: DMA straight into it
@@ -292,25 +330,61 @@ struct VecEnv {
         LaunchCtx lc;
 #ifndef PG_HOSTSIM
         lc.stream = stream;
+        lc.ticket = d_tickets;
+        lc.max_logic_blocks = max_logic_blocks;
 #endif
         lc.launch_counter = &launches;
         return lc;
     }
 
+    // One step = for every (game, env chunk): logic kernel then render kernel. Chunks go round-robin
+    // onto a few auxiliary streams forked from / joined to the handle's stream with events, so the
+    // latency-bound logic kernel of one chunk overlaps the issue-bound render kernel of another on
+    // the same SMs (the two kernels stress different limits; back to back they leave both idle).
     void launch(bool init) {
         const int G = (int)games.size();
-        for (int g = 0; g < G; g++) {
-            KParams p = base;
-            p.assets = d_assets[g];
-            p.game_id = games[g]->id;
-            p.env_first = g;
-            p.env_step = G;
-            p.env_count = num_envs / G;
-            if (init)
-                games[g]->init(p, lctx());
-            else
-                games[g]->step(p, lctx());
+        const int per_game = num_envs / G;
+        int chunks = kChunks;
+        if (per_game < 4096 * chunks)
+            chunks = 1;
+#ifndef PG_HOSTSIM
+        const int nstreams = chunks > 1 ? kAuxStreams : 0;
+        if (nstreams) {
+            CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+            for (int s = 0; s < nstreams; s++) CUDA_CHECK(cudaStreamWaitEvent(aux[s], ev_fork, 0));
         }
+#endif
+        int k = 0;
+        for (int g = 0; g < G; g++) {
+            for (int cidx = 0; cidx < chunks; cidx++, k++) {
+                const int lo = (int)((int64_t)per_game * cidx / chunks);
+                const int hi = (int)((int64_t)per_game * (cidx + 1) / chunks);
+                KParams p = base;
+                p.assets = d_assets[g];
+                p.game_id = games[g]->id;
+                p.env_first = g + lo * G;
+                p.env_step = G;
+                p.env_count = hi - lo;
+                LaunchCtx lc = lctx();
+#ifndef PG_HOSTSIM
+                if (nstreams)
+                    lc.stream = aux[k % nstreams];
+                lc.ticket = d_tickets + (k % kMaxTickets);
+#endif
+                if (init)
+                    games[g]->init(p, lc);
+                else
+                    games[g]->step(p, lc);
+            }
+        }
+#ifndef PG_HOSTSIM
+        if (nstreams) {
+            for (int s = 0; s < nstreams; s++) {
+                CUDA_CHECK(cudaEventRecord(ev_join[s], aux[s]));
+                CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join[s], 0));
+            }
+        }
+#endif
     }
 
     void ensure_initial_reset() {
@@ -492,6 +566,17 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     v->set_device();
     CUDA_CHECK(cudaStreamCreateWithFlags(&v->own_stream, cudaStreamNonBlocking));
     v->stream = v->own_stream;
+    for (int s = 0; s < VecEnv::kAuxStreams; s++) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&v->aux[s], cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&v->ev_join[s], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming));
+    {
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, v->device));
+        v->max_logic_blocks = prop.multiProcessorCount * PG_LOGIC_MIN_BLOCKS;
+        CUDA_CHECK(cudaMalloc((void **)&v->d_tickets, VecEnv::kMaxTickets * sizeof(unsigned int)));
+    }
     // sub_step <-> push_obj recurse to depth 5 on the logic thread
     CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
 #else
@@ -553,6 +638,7 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     p.info_prev_level_seed = dev_alloc<int32_t>(N);
     p.info_prev_level_complete = dev_alloc<uint8_t>(N);
     p.info_level_seed = dev_alloc<int32_t>(N);
+    p.dbg_cycles = getenv("PGB200_DEBUG_TIMING") ? dev_alloc<uint32_t>(N) : nullptr;
 
     // ---- per-env seed chain (vecgame.cpp:301-314), replayed for the global env indices
     {
@@ -748,6 +834,10 @@ void libenv_close(libenv_env *handle) {
     dev_free(p.info_prev_level_complete);
     dev_free(p.info_level_seed);
     dev_free(v->d_lvl_seeds);
+#ifndef PG_HOSTSIM
+    if (v->d_tickets)
+        cudaFree(v->d_tickets);
+#endif
     for (auto a : v->d_assets) dev_free(a);
     host_free(v->st_rgb);
 #ifndef PG_HOSTSIM
@@ -761,6 +851,14 @@ void libenv_close(libenv_env *handle) {
     host_free(v->st_prev_complete);
     host_free(v->st_seed);
 #ifndef PG_HOSTSIM
+    for (int s = 0; s < VecEnv::kAuxStreams; s++) {
+        if (v->aux[s])
+            cudaStreamDestroy(v->aux[s]);
+        if (v->ev_join[s])
+            cudaEventDestroy(v->ev_join[s]);
+    }
+    if (v->ev_fork)
+        cudaEventDestroy(v->ev_fork);
     if (v->own_stream)
         cudaStreamDestroy(v->own_stream);
 #endif
@@ -831,6 +929,18 @@ uint32_t pgb200_get_errors(libenv_env *handle, uint32_t *host_out) {
         any |= hdr[e].err;
     }
     return any;
+}
+
+int pgb200_debug_cycles(libenv_env *handle, uint32_t *host_out) {
+    VecEnv *v = (VecEnv *)handle;
+    if (!v->base.dbg_cycles)
+        return -1;
+    v->set_device();
+    v->sync();
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMemcpy(host_out, v->base.dbg_cycles, (size_t)v->num_envs * 4, cudaMemcpyDeviceToHost));
+#endif
+    return 0;
 }
 
 int64_t pgb200_kernel_launches(libenv_env *handle) { return ((VecEnv *)handle)->launches; }

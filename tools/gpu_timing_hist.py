@@ -1,0 +1,24 @@
+"""Per-env logic duration histogram (needs PGB200_DEBUG_TIMING=1)."""
+import os, sys
+os.environ["PGB200_DEBUG_TIMING"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from procgen_b200 import ProcgenGym3Env
+game = sys.argv[1] if len(sys.argv) > 1 else "coinrun"
+mode = sys.argv[2] if len(sys.argv) > 2 else "easy"
+n = 65536
+env = ProcgenGym3Env(n, game, distribution_mode=mode, num_levels=0, rand_seed=0)
+g = torch.Generator(device="cuda").manual_seed(0)
+for t in range(60):
+    env.act(torch.randint(0, 15, (n,), device="cuda", dtype=torch.int32, generator=g))
+rew, ob, first = env.observe()
+torch.cuda.synchronize()
+cyc = np.zeros(n, np.uint32)
+assert env._lib.pgb200_debug_cycles(env._h, cyc.ctypes.data) == 0
+first = first.cpu().numpy()
+print("envs", n, "resets this step", int(first.sum()))
+for name, sel in [("no-reset", ~first), ("reset", first)]:
+    c = cyc[sel]
+    if len(c):
+        print(name, "n", len(c), "mean %.0f" % c.mean(), "p50 %.0f p90 %.0f p99 %.0f max %.0f cycles" % tuple(np.percentile(c, [50, 90, 99, 100])))
+print("sum cycles / (148 SMs * 48 warps) = %.0f cycles ~ %.2f ms at 1.9 GHz" % (cyc.sum() / (148 * 48), cyc.sum() / (148 * 48) / 1.9e6))
