@@ -353,7 +353,7 @@ static void draw_scaled(QImage *dev, const QImage &img, QRectF tr, int int_opaci
         double h = qRound(tr.y() + tr.height() - y);
         tr = QRectF(x, y, w, h);
     }
-    if (tr.width() <= 0 || tr.height() <= 0)
+    if (tr.width() == 0 || tr.height() == 0)
         return;
     int ix, iy, dstx, dsty;
     int tx1, ty1, tx2, ty2, h, w;
@@ -362,8 +362,20 @@ static void draw_scaled(QImage *dev, const QImage &img, QRectF tr, int int_opaci
         const char *e = getenv("QT_SHIM_SCALE_VARIANT");
         variant = e ? atoi(e) : 1;
     }
-    tx1 = qRound(tr.x()), ty1 = qRound(tr.y());
-    tx2 = qRound(tr.x() + tr.width()), ty2 = qRound(tr.y() + tr.height());
+    {
+        // targetRect.normalized().toRect()
+        double nx = tr.x(), ny = tr.y(), nw = tr.width(), nh = tr.height();
+        if (nw < 0) {
+            nx += nw;
+            nw = -nw;
+        }
+        if (nh < 0) {
+            ny += nh;
+            nh = -nh;
+        }
+        tx1 = qRound(nx), ty1 = qRound(ny);
+        tx2 = qRound(nx + nw), ty2 = qRound(ny + nh);
+    }
     tx1 = std::max(tx1, 0);
     ty1 = std::max(ty1, 0);
     tx2 = std::min(tx2, dev->w);
@@ -386,11 +398,25 @@ static void draw_scaled(QImage *dev, const QImage &img, QRectF tr, int int_opaci
         const double sy = double(sh) / tr.height();
         ix = int(0x00010000 * sx);
         iy = int(0x00010000 * sy);
-        dstx = int(ceil((tx1 + 0.5 - tr.x()) * sx * 65536)) - 1;
-        dsty = int(ceil((ty1 + 0.5 - tr.y()) * sy * 65536)) - 1;
+        if (sx < 0)  // mirrored: measured from the rect's right() = x + w, source from its right end
+            dstx = int(floor((tx1 + 0.5 - (tr.x() + tr.width())) * sx * 65536)) + 1 + sw * 65536;
+        else
+            dstx = int(ceil((tx1 + 0.5 - tr.x()) * sx * 65536)) - 1;
+        if (sy < 0)
+            dsty = int(floor((ty1 + 0.5 - (tr.y() + tr.height())) * sy * 65536)) + 1 + sh * 65536;
+        else
+            dsty = int(ceil((ty1 + 0.5 - tr.y()) * sy * 65536)) - 1;
     }
     uint32_t basex = uint32_t(dstx);
     uint32_t srcy = uint32_t(dsty);
+    if (int(srcy >> 16) >= sh && iy < 0) {
+        srcy += iy;
+        --h;
+    }
+    if (int(basex >> 16) >= sw && ix < 0) {
+        basex += ix;
+        --w;
+    }
 
     // Qt's guard against a last row/column sampled just outside the source
     int yend = int(srcy + uint32_t(iy) * uint32_t(h - 1)) >> 16;
@@ -594,20 +620,132 @@ static inline int FloatToQ16Dot16(double i) { return int(i * 65536.); }
 static inline double qBoundD(double lo, double v, double hi) { return std::max(lo, std::min(hi, v)); }
 
 // QRasterizer::rasterizeLine(a, b, width), non-antialiased, clip = device rect
+struct ScanLine {
+    int x, delta, top, bottom, winding;
+};
+
+static void scan_convert_quad(const SpanSink &sink, const double *vx, const double *vy) {
+    const int W = sink.dev->w, H = sink.dev->h;
+    long X[4], Y[4];
+    for (int i = 0; i < 4; i++) {
+        X[i] = (long)((vx[i] - 0.5) * 64);
+        Y[i] = (long)((vy[i] - 0.5) * 64);
+    }
+    ScanLine lines[4];
+    int n = 0;
+    for (int i = 0; i < 4; i++) {
+        long ax = X[i], ay = Y[i], bx = X[(i + 1) & 3], by = Y[(i + 1) & 3];
+        if (ax == bx && ay == by)
+            continue;
+        int winding = 1;
+        if (ay > by) {
+            std::swap(ax, bx);
+            std::swap(ay, by);
+            winding = -1;
+        }
+        ax += 32; ay += 32; bx += 32; by += 32;  // COORD_OFFSET
+        int iTop = std::max(0, int((ay + 32 - 1) >> 6));
+        int iBottom = std::min(H - 1, int((by - 32 - 1) >> 6));
+        if (iTop <= iBottom) {
+            int aFP = 0x8000 + int(ax * 1024) - 1;
+            if (bx == ax) {
+                lines[n++] = ScanLine{aFP, 0, iTop, iBottom, winding};
+            } else {
+                const double slope = (bx - ax) / double(by - ay);
+                const int slopeFP = int(slope * 65536.);
+                const long long dy = (long long)(iTop << 16) + 0x8000 - (long long)ay * 1024;
+                int xFP = aFP + int(((long long)slopeFP * dy) >> 16);
+                lines[n++] = ScanLine{xFP, slopeFP, iTop, iBottom, winding};
+            }
+        }
+    }
+    if (n == 0)
+        return;
+    std::stable_sort(lines, lines + n, [](const ScanLine &a, const ScanLine &b) { return a.top < b.top; });
+    ScanLine *active[4];
+    int na = 0, li = 0;
+    for (int y = lines[0].top; y < H; ++y) {
+        for (; li < n && lines[li].top == y; ++li) active[na++] = &lines[li];
+        if (na == 0 && li >= n)
+            break;
+        for (int i = 1; i < na; ++i) {
+            ScanLine *t = active[i];
+            int j = i;
+            while (j > 0 && active[j - 1]->x > t->x) {
+                active[j] = active[j - 1];
+                --j;
+            }
+            active[j] = t;
+        }
+        int x = 0, winding = 0;
+        int keep = 0;
+        ScanLine *next_active[4];
+        for (int i = 0; i < na; ++i) {
+            ScanLine *node = active[i];
+            const int current = node->x >> 16;
+            if (winding & 1) {
+                int x0 = std::max(x, 0), x1 = std::min(current, W);
+                if (x1 > x0)
+                    sink.span(x0, x1 - x0, y);
+            }
+            x = current;
+            winding += node->winding;
+            if (node->bottom != y) {
+                node->x += node->delta;
+                next_active[keep++] = node;
+            }
+        }
+        for (int i = 0; i < keep; i++) active[i] = next_active[i];
+        na = keep;
+    }
+}
+
 static void rasterize_line(const SpanSink &sink, double ax, double ay, double bx, double by, double width) {
     const int clipL = 0, clipT = 0, clipR = sink.dev->w - 1, clipB = sink.dev->h - 1;  // inclusive QRect edges
     if ((ax == bx && ay == by) || width == 0)
         return;
     double pax = ax, pay = ay, pbx = bx, pby = by;
     {
-        static double off = -1e9;
-        if (off < -1e8) {
-            const char *e = getenv("QT_SHIM_LINE_OFFSET");
-            off = e ? atof(e) : 0.0;
+        // clip the segment to the device rect grown by the line's half extent
+        const double offx = fabs(by - ay) * width * 0.5, offy = fabs(bx - ax) * width * 0.5;
+        const double cl = clipL - offx, ct = clipT - offy, cr = (clipR + 1) + offx, cb = (clipB + 1) + offy;
+        auto inside = [&](double x, double y) { return !(x < cl || x > cr || y < ct || y > cb); };
+        if (!inside(pax, pay) || !inside(pbx, pby)) {
+            double t1 = 0, t2 = 1;
+            const double o[2] = {pax, pay};
+            const double dd[2] = {pbx - pax, pby - pay};
+            const double low[2] = {cl, ct};
+            const double high[2] = {cr, cb};
+            for (int i = 0; i < 2; ++i) {
+                if (dd[i] == 0) {
+                    if (o[i] <= low[i] || o[i] >= high[i])
+                        return;
+                    continue;
+                }
+                const double d_inv = 1 / dd[i];
+                double t_low = (low[i] - o[i]) * d_inv;
+                double t_high = (high[i] - o[i]) * d_inv;
+                if (t_low > t_high)
+                    std::swap(t_low, t_high);
+                if (t1 < t_low)
+                    t1 = t_low;
+                if (t2 > t_high)
+                    t2 = t_high;
+                if (t1 >= t2)
+                    return;
+            }
+            const double npax = pax + (pbx - pax) * t1, npay = pay + (pby - pay) * t1;
+            const double npbx = pax + (pbx - pax) * t2, npby = pay + (pby - pay) * t2;
+            pax = npax; pay = npay; pbx = npbx; pby = npby;
         }
-        pax += off; pay += off; pbx += off; pby += off;
+        const double d0x = ax - bx, d0y = ay - by;
+        const double w0 = d0x * d0x + d0y * d0y;
+        const double d1x = pax - pbx, d1y = pay - pby;
+        const double w = d1x * d1x + d1y * d1y;
+        if (w == 0)
+            return;
+        width *= sqrt(w0 / w);
     }
-    // (clipping of far-away endpoints is skipped: sprites are at most a few device pixels off screen)
     if (q26Dot6Compare(pay, pby)) {
         const double x = (pax + pbx) * 0.5f;
         const double dx = fabs(pbx - pax) * 0.5f;
@@ -660,56 +798,10 @@ static void rasterize_line(const SpanSink &sink, double ax, double ay, double bx
         rightx = pax + perpx; righty = pay + perpy;
         bottomx = pbx + perpx; bottomy = pby + perpy;
     }
-    const double topLeftSlope = qSafeDivide(leftx - topx, lefty - topy);
-    const double bottomLeftSlope = qSafeDivide(bottomx - leftx, bottomy - lefty);
-    const double topRightSlope = qSafeDivide(rightx - topx, righty - topy);
-    const double bottomRightSlope = qSafeDivide(bottomx - rightx, bottomy - righty);
-    const int topLeftSlopeFP = qSafeFloatToQ16Dot16(topLeftSlope);
-    const int topRightSlopeFP = qSafeFloatToQ16Dot16(topRightSlope);
-    const int bottomLeftSlopeFP = qSafeFloatToQ16Dot16(bottomLeftSlope);
-    const int bottomRightSlopeFP = qSafeFloatToQ16Dot16(bottomRightSlope);
-
-    static double oT = 0, oB = 0, oL = 0, oR = 0, oS = 0;
-    static bool init = false;
-    if (!init) {
-        init = true;
-        const char *e = getenv("QT_SHIM_EDGE_OFFSETS");
-        if (e) sscanf(e, "%lf,%lf,%lf,%lf,%lf", &oT, &oB, &oL, &oR, &oS);
-    }
-    int iTop = int(topy + 0.5f + oT);
-    int iLeft = lefty + oB < 0.5f ? -1 : int(lefty - 0.5f + oB);
-    int iRight = righty + oB < 0.5f ? -1 : int(righty - 0.5f + oB);
-    int iBottom = bottomy + oB < 0.5f ? -1 : int(bottomy - 0.5f + oB);
-    int iMiddle = std::min(iLeft, iRight);
-
-    int leftIntersectAf = FloatToQ16Dot16(topx + 0.5f + oL + (iTop + 0.5f + oS - topy) * topLeftSlope);
-    int leftIntersectBf = FloatToQ16Dot16(leftx + 0.5f + oL + (iLeft + 1.5f + oS - lefty) * bottomLeftSlope);
-    int rightIntersectAf = FloatToQ16Dot16(topx - 0.5f + oR + (iTop + 0.5f + oS - topy) * topRightSlope);
-    int rightIntersectBf = FloatToQ16Dot16(rightx - 0.5f + oR + (iRight + 1.5f + oS - righty) * bottomRightSlope);
-
-    int y = iTop;
-    auto segment = [&](int next, int &li, int &ri, int ls, int rs) {
-        int ny = std::min(next + 1, clipT);
-        if (y < ny) {
-            li += ls * (ny - y);
-            ri += rs * (ny - y);
-            y = ny;
-        }
-        if (next > clipB)
-            next = clipB;
-        for (; y <= next; ++y) {
-            const int x1 = std::max(li >> 16, clipL);
-            const int x2 = std::min(ri >> 16, clipR);
-            if (x2 >= x1)
-                sink.span(x1, x2 - x1 + 1, y);
-            li += ls;
-            ri += rs;
-        }
-    };
-    segment(iMiddle, leftIntersectAf, rightIntersectAf, topLeftSlopeFP, topRightSlopeFP);
-    segment(iRight, leftIntersectBf, rightIntersectAf, bottomLeftSlopeFP, topRightSlopeFP);
-    segment(iLeft, leftIntersectAf, rightIntersectBf, topLeftSlopeFP, bottomRightSlopeFP);
-    segment(iBottom, leftIntersectBf, rightIntersectBf, bottomLeftSlopeFP, bottomRightSlopeFP);
+    // general case: the four corners go through the aliased scan converter
+    const double vx[4] = {topx, rightx, bottomx, leftx};
+    const double vy[4] = {topy, righty, bottomy, lefty};
+    scan_convert_quad(sink, vx, vy);
 }
 
 static void draw_rotated(QImage *dev, const QImage &img, const QRectF &r, const Xform &m, int int_opacity) {
@@ -757,13 +849,14 @@ static void draw_rotated(QImage *dev, const QImage &img, const QRectF &r, const 
     sink.m22 = c11 * dinv;
     sink.dx = (c21 * pdy - c22 * pdx) * dinv;
     sink.dy = (c12 * pdx - c11 * pdy) * dinv;
-    // a, b = matrix.map of the mid points of the left and right edges of r
-    double lx = r.x(), ly = (r.y() + (r.y() + r.height())) * 0.5f;
-    double rx = r.x() + r.width(), ry = ly;
-    lx = (r.x() + r.x()) * 0.5f;
-    rx = ((r.x() + r.width()) + (r.x() + r.width())) * 0.5f;
+    // Coverage: QRasterizer::rasterizeLine on the segment joining the mid points of the left and
+    // right edges of r (what QRasterPaintEngine::drawImage does for shear-free transforms): exact
+    // axis-aligned branch, otherwise the aliased scan converter on the four corners.
+    double ly = (r.y() + (r.y() + r.height())) * 0.5f;
+    double lx = (r.x() + r.x()) * 0.5f;
+    double rx = ((r.x() + r.width()) + (r.x() + r.width())) * 0.5f;
     double ax = m.m11 * lx + m.m21 * ly + m.dx, ay = m.m12 * lx + m.m22 * ly + m.dy;
-    double bx = m.m11 * rx + m.m21 * ry + m.dx, by = m.m12 * rx + m.m22 * ry + m.dy;
+    double bx = m.m11 * rx + m.m21 * ly + m.dx, by = m.m12 * rx + m.m22 * ly + m.dy;
     rasterize_line(sink, ax, ay, bx, by, r.height() / r.width());
 }
 
@@ -772,6 +865,11 @@ void QPainter::drawImage(const QRectF &target, const QImage &image) {
     int io = int(d->cur.opacity * 256);
     if (!m.rotated) {
         draw_scaled(d->dev, image, QRectF(target.x() + m.dx, target.y() + m.dy, target.width(), target.height()), io);
+    } else if (fabs(m.m12) <= 1e-12 && fabs(m.m21) <= 1e-12) {
+        // QTransform::type() is fuzzy (qFuzzyIsNull): rotate(+-180) classifies as TxScale and takes the
+        // scaling blit with qt_mapRect_non_normalizing; width/height may be negative
+        draw_scaled(d->dev, image,
+                    QRectF(m.m11 * target.x() + m.dx, m.m22 * target.y() + m.dy, m.m11 * target.width(), m.m22 * target.height()), io);
     } else {
         draw_rotated(d->dev, image, target, m, io);
     }

@@ -15,6 +15,7 @@ struct BigFish : Defaults<BigFish>, DrawDefaults<BigFish> {
     static constexpr int GRID_CAP = 20 * 20;
     static constexpr int SCRATCH_WORDS = 0;
     static constexpr int MAX_VISIBLE_ENTS = 64;
+    static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "bigfish";
 

@@ -17,6 +17,7 @@ struct HeistGame : Defaults<HeistGame>, DrawDefaults<HeistGame> {
     static constexpr int GRID_CAP = 23 * 23;
     static constexpr int SCRATCH_WORDS = 8192;   // MazeGen::words_needed(23) = 6717
     static constexpr int MAX_VISIBLE_ENTS = 64;
+    static constexpr int MAX_ROT_BLITS = 8;
     static constexpr int MAX_VIEW_CELLS = 13;    // hard: whole 13x13 world; memory mode is centred (11)
     static constexpr const char *NAME = "heist";
 

@@ -16,6 +16,7 @@ struct MazeGame : Defaults<MazeGame>, DrawDefaults<MazeGame> {
     static constexpr int GRID_CAP = 31 * 31;
     static constexpr int SCRATCH_WORDS = 12288;  // MazeGen::words_needed(31) = 11761
     static constexpr int MAX_VISIBLE_ENTS = 64;
+    static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 25;    // hard: whole 25x25 world; memory mode is centred (11)
     static constexpr const char *NAME = "maze";
 

@@ -199,7 +199,7 @@ PG_HD void env_render_quad(const KParams &p, int env, const Frame &f, int quad) 
 // Frame sizing per game: visible window (cells per side) and entity capacity.
 template <class G>
 struct FrameFor {
-    using type = FrameT<G::MAX_VIEW_CELLS, G::MAX_VISIBLE_ENTS>;
+    using type = FrameT<G::MAX_VIEW_CELLS, G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
 };
 
 }  // namespace pg

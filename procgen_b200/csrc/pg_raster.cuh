@@ -25,7 +25,7 @@
 
 namespace pg {
 
-enum BlitKind : uint8_t { BLIT_NONE = 0, BLIT_IMAGE = 1, BLIT_SOLID = 2 };
+enum BlitKind : uint8_t { BLIT_NONE = 0, BLIT_IMAGE = 1, BLIT_SOLID = 2, BLIT_ROTATED = 3 };
 
 struct Blit {
     uint8_t x1, y1, w, h;    // device pixels [x1,x1+w) x [y1,y1+h) after clip + Qt's edge guards;
@@ -40,6 +40,16 @@ struct Blit {
 };
 static_assert(sizeof(Blit) == 32, "Blit is 32 B");
 
+// Extra record of a rotated sprite (Blit.kind == BLIT_ROTATED, Blit.ix = index): per device row the
+// covered span, plus the texel map of whichever of Qt's two transformed-image paths applies.
+struct RotBlit {
+    uint8_t x1[RES_H], x2[RES_H];  // row y covers [x1[y], x2[y]); x2 <= x1: nothing
+    int32_t absolute;               // 1: qt_transform_image (u = px*dudx + py*dudy + u0); 0: fetchTransformed
+    int32_t dudx, dvdx, dudy, dvdy, u0, v0;  // absolute map; span-relative uses dudx,dvdx as fdx,fdy
+    int32_t pad;
+    double m11, m12, m21, m22, dx, dy;       // inverse matrix for the span-start texel (fetchTransformed)
+};
+
 constexpr int MAX_BG_BLITS = 8;
 constexpr int MAX_OVERLAY_BLITS = 8;
 
@@ -48,9 +58,12 @@ struct Camera {
     float unit, view_dim, x_off, y_off;
 };
 
-template <int MAX_CELLS_1D, int MAX_ENT_BLITS>
+template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
 struct FrameT {
     static constexpr int kMaxCells1D = MAX_CELLS_1D;
+    static constexpr int kMaxRot = MAX_ROT_BLITS > 0 ? MAX_ROT_BLITS : 1;
+    int32_t n_rot;
+    RotBlit rot[MAX_ROT_BLITS > 0 ? MAX_ROT_BLITS : 1];
     static constexpr int kMaxEntBlits = MAX_ENT_BLITS;   // VISIBLE entity blits (after culling)
     Camera cam;
     int32_t low_x, low_y, nx, ny;   // visible grid window: cells [low_x, low_x+nx) x [low_y, low_y+ny)
@@ -95,15 +108,19 @@ PG_HD void make_image_blit(Blit &b, double tx, double ty, double tw, double th, 
         tw = w;
         th = h;
     }
-    if (!(tw > 0) || !(th > 0))
+    if (tw == 0 || th == 0 || tw != tw || th != th)
         return;
-    // Qt 6.6.3 qt_scale_image_32bit: step and start both come from the source/target ratio in double
+    // Qt 6.6.3 qt_scale_image_32bit: step and start both come from the source/target ratio in double.
+    // Negative sizes (a mirroring scale, e.g. rotate(180)) step backwards from the far source edge.
     const double sx = (double)sw / tw;
     const double sy = (double)sh / th;
     const int ix = (int)(65536.0 * sx);
     const int iy = (int)(65536.0 * sy);
-    int tx1 = pg_qround(tx), ty1 = pg_qround(ty);
-    int tx2 = pg_qround(tx + tw), ty2 = pg_qround(ty + th);
+    double nx = tx, ny = ty, nw = tw, nh = th;  // targetRect.normalized()
+    if (nw < 0) { nx += nw; nw = -nw; }
+    if (nh < 0) { ny += nh; nh = -nh; }
+    int tx1 = pg_qround(nx), ty1 = pg_qround(ny);
+    int tx2 = pg_qround(nx + nw), ty2 = pg_qround(ny + nh);
     if (tx1 < 0) tx1 = 0;
     if (ty1 < 0) ty1 = 0;
     if (tx2 > RES_W) tx2 = RES_W;
@@ -112,10 +129,27 @@ PG_HD void make_image_blit(Blit &b, double tx, double ty, double tw, double th, 
         return;
     int h = ty2 - ty1;
     int w = tx2 - tx1;
-    const int dstx = (int)pg_dceil((tx1 + 0.5 - tx) * sx * 65536) - 1;
-    const int dsty = (int)pg_dceil((ty1 + 0.5 - ty) * sy * 65536) - 1;
-    const uint32_t basex = (uint32_t)dstx;
-    const uint32_t srcy = (uint32_t)dsty;
+    int dstx, dsty;
+    if (sx < 0)
+        dstx = (int)pg_dfloor((tx1 + 0.5 - (tx + tw)) * sx * 65536) + 1 + sw * 65536;
+    else
+        dstx = (int)pg_dceil((tx1 + 0.5 - tx) * sx * 65536) - 1;
+    if (sy < 0)
+        dsty = (int)pg_dfloor((ty1 + 0.5 - (ty + th)) * sy * 65536) + 1 + sh * 65536;
+    else
+        dsty = (int)pg_dceil((ty1 + 0.5 - ty) * sy * 65536) - 1;
+    uint32_t basex = (uint32_t)dstx;
+    uint32_t srcy = (uint32_t)dsty;
+    if ((int)(srcy >> 16) >= sh && iy < 0) {
+        srcy += (uint32_t)iy;
+        --h;
+    }
+    if ((int)(basex >> 16) >= sw && ix < 0) {
+        basex += (uint32_t)ix;
+        --w;
+    }
+    if (w <= 0 || h <= 0)
+        return;
     int yend = ((int)(srcy + (uint32_t)iy * (uint32_t)(h - 1))) >> 16;
     if (yend < 0 || yend >= sh)
         --h;
@@ -138,6 +172,368 @@ PG_HD void make_image_blit(Blit &b, double tx, double ty, double tw, double th, 
     b.src = sd.off;
     b.sw = (uint16_t)sw;
     b.sh = (uint16_t)sh;
+}
+
+
+// ================================================================= rotated sprites
+// Device twin of oracle/shim/qt_raster.cpp's transformed-image restatement (see there for the Qt
+// provenance of every rule): per-row spans + a texel map, built once per rotated sprite.
+struct RotXform {
+    double m11, m12, m21, m22, dx, dy;  // Qt convention: x' = m11*x + m21*y + dx ; y' = m12*x + m22*y + dy
+};
+
+PG_HD void rot_span(RotBlit &rb, int x, int len, int y) {
+    if (y < 0 || y >= RES_H)
+        return;
+    if (x < 0) {
+        len += x;
+        x = 0;
+    }
+    if (x + len > RES_W)
+        len = RES_W - x;
+    if (len <= 0)
+        return;
+    if (rb.x2[y] <= rb.x1[y]) {
+        rb.x1[y] = (uint8_t)x;
+        rb.x2[y] = (uint8_t)(x + len);
+    } else {  // a second span on a row of a convex quad: keep the union
+        if (x < rb.x1[y]) rb.x1[y] = (uint8_t)x;
+        if (x + len > rb.x2[y]) rb.x2[y] = (uint8_t)(x + len);
+    }
+}
+
+// QScanConverter on a quad: vertices shifted by -0.5, truncated to 26.6, edges stepped in 16.16
+PG_HD void rot_scan_convert_quad(RotBlit &rb, const double *vx, const double *vy) {
+    long long X[4], Y[4];
+    for (int i = 0; i < 4; i++) {
+        X[i] = (long long)((vx[i] - 0.5) * 64);
+        Y[i] = (long long)((vy[i] - 0.5) * 64);
+    }
+    int lx[4], ldelta[4], ltop[4], lbottom[4], lwind[4];
+    int n = 0;
+    for (int i = 0; i < 4; i++) {
+        long long ax = X[i], ay = Y[i], bx = X[(i + 1) & 3], by = Y[(i + 1) & 3];
+        if (ax == bx && ay == by)
+            continue;
+        int winding = 1;
+        if (ay > by) {
+            long long t = ax; ax = bx; bx = t;
+            t = ay; ay = by; by = t;
+            winding = -1;
+        }
+        ax += 32; ay += 32; bx += 32; by += 32;
+        int iTop = (int)((ay + 32 - 1) >> 6);
+        if (iTop < 0) iTop = 0;
+        int iBottom = (int)((by - 32 - 1) >> 6);
+        if (iBottom > RES_H - 1) iBottom = RES_H - 1;
+        if (iTop <= iBottom) {
+            int aFP = 0x8000 + (int)(ax * 1024) - 1;
+            if (bx == ax) {
+                lx[n] = aFP; ldelta[n] = 0;
+            } else {
+                const double slope = (double)(bx - ax) / (double)(by - ay);
+                const int slopeFP = (int)(slope * 65536.);
+                const long long dy = (long long)(iTop << 16) + 0x8000 - ay * 1024;
+                lx[n] = aFP + (int)(((long long)slopeFP * dy) >> 16);
+                ldelta[n] = slopeFP;
+            }
+            ltop[n] = iTop; lbottom[n] = iBottom; lwind[n] = winding;
+            n++;
+        }
+    }
+    if (n == 0)
+        return;
+    // stable sort by top (n <= 4)
+    int order[4];
+    for (int i = 0; i < n; i++) order[i] = i;
+    for (int i = 1; i < n; i++) {
+        int t = order[i], j = i;
+        while (j > 0 && ltop[order[j - 1]] > ltop[t]) {
+            order[j] = order[j - 1];
+            --j;
+        }
+        order[j] = t;
+    }
+    int active[4];
+    int na = 0, li = 0;
+    for (int y = ltop[order[0]]; y < RES_H; ++y) {
+        for (; li < n && ltop[order[li]] == y; ++li) active[na++] = order[li];
+        if (na == 0 && li >= n)
+            break;
+        for (int i = 1; i < na; ++i) {
+            int t = active[i], j = i;
+            while (j > 0 && lx[active[j - 1]] > lx[t]) {
+                active[j] = active[j - 1];
+                --j;
+            }
+            active[j] = t;
+        }
+        int x = 0, winding = 0, keep = 0;
+        int nexta[4];
+        for (int i = 0; i < na; ++i) {
+            const int node = active[i];
+            const int current = lx[node] >> 16;
+            if (winding & 1) {
+                int x0 = x < 0 ? 0 : x, x1 = current > RES_W ? RES_W : current;
+                if (x1 > x0)
+                    rot_span(rb, x0, x1 - x0, y);
+            }
+            x = current;
+            winding += lwind[node];
+            if (lbottom[node] != y) {
+                lx[node] += ldelta[node];
+                nexta[keep++] = node;
+            }
+        }
+        for (int i = 0; i < keep; i++) active[i] = nexta[i];
+        na = keep;
+    }
+}
+
+PG_HD bool rot_q26Dot6Compare(double p1, double p2) { return (int)((p2 - p1) * 64.) == 0; }
+PG_HD double rot_bound(double lo, double v, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// QRasterizer::rasterizeLine(a, b, width), non-antialiased, clip = the 64x64 device
+PG_HD void rot_rasterize_line(RotBlit &rb, double ax, double ay, double bx, double by, double width) {
+    const int clipL = 0, clipT = 0, clipR = RES_W - 1, clipB = RES_H - 1;
+    if ((ax == bx && ay == by) || width == 0)
+        return;
+    double pax = ax, pay = ay, pbx = bx, pby = by;
+    {
+        const double offx = pg_dfabs(by - ay) * width * 0.5, offy = pg_dfabs(bx - ax) * width * 0.5;
+        const double cl = clipL - offx, ct = clipT - offy, cr = (clipR + 1) + offx, cb = (clipB + 1) + offy;
+        const bool a_in = !(pax < cl || pax > cr || pay < ct || pay > cb);
+        const bool b_in = !(pbx < cl || pbx > cr || pby < ct || pby > cb);
+        if (!a_in || !b_in) {
+            double t1 = 0, t2 = 1;
+            const double o[2] = {pax, pay};
+            const double dd[2] = {pbx - pax, pby - pay};
+            const double low[2] = {cl, ct};
+            const double high[2] = {cr, cb};
+            for (int i = 0; i < 2; ++i) {
+                if (dd[i] == 0) {
+                    if (o[i] <= low[i] || o[i] >= high[i])
+                        return;
+                    continue;
+                }
+                const double d_inv = 1 / dd[i];
+                double t_low = (low[i] - o[i]) * d_inv;
+                double t_high = (high[i] - o[i]) * d_inv;
+                if (t_low > t_high) {
+                    double t = t_low; t_low = t_high; t_high = t;
+                }
+                if (t1 < t_low) t1 = t_low;
+                if (t2 > t_high) t2 = t_high;
+                if (t1 >= t2)
+                    return;
+            }
+            const double npax = pax + (pbx - pax) * t1, npay = pay + (pby - pay) * t1;
+            const double npbx = pax + (pbx - pax) * t2, npby = pay + (pby - pay) * t2;
+            pax = npax; pay = npay; pbx = npbx; pby = npby;
+        }
+        const double d0x = ax - bx, d0y = ay - by;
+        const double w0 = d0x * d0x + d0y * d0y;
+        const double d1x = pax - pbx, d1y = pay - pby;
+        const double w = d1x * d1x + d1y * d1y;
+        if (w == 0)
+            return;
+        width *= pg_dsqrt(w0 / w);
+    }
+    if (rot_q26Dot6Compare(pay, pby)) {
+        const double x = (pax + pbx) * 0.5f;
+        const double dx = pg_dfabs(pbx - pax) * 0.5f;
+        const double y = pay;
+        const double dy = width * dx;
+        pax = x; pay = y - dy;
+        pbx = x; pby = y + dy;
+        width = 1 / width;
+    }
+    if (rot_q26Dot6Compare(pax, pbx)) {
+        if (pay > pby) {
+            double t = pax; pax = pbx; pbx = t;
+            t = pay; pay = pby; pby = t;
+        }
+        const double dy = pby - pay;
+        const double halfWidth = 0.5f * width * dy;
+        double left = pax - halfWidth;
+        double right = pax + halfWidth;
+        left = rot_bound((double)clipL, left, (double)(clipR + 1));
+        right = rot_bound((double)clipL, right, (double)(clipR + 1));
+        pay = rot_bound((double)clipT, pay, (double)(clipB + 1));
+        pby = rot_bound((double)clipT, pby, (double)(clipB + 1));
+        if (rot_q26Dot6Compare(left, right) || rot_q26Dot6Compare(pay, pby))
+            return;
+        int iTop = (int)(pay + 0.5f);
+        int iBottom = pby < 0.5f ? -1 : (int)(pby - 0.5f);
+        int iLeft = (int)(left + 0.5f);
+        int iRight = right < 0.5f ? -1 : (int)(right - 0.5f);
+        int iWidth = iRight - iLeft + 1;
+        for (int y = iTop; y <= iBottom; ++y) rot_span(rb, iLeft, iWidth, y);
+        return;
+    }
+    if (pay > pby) {
+        double t = pax; pax = pbx; pbx = t;
+        t = pay; pay = pby; pby = t;
+    }
+    const double deltax = (pbx - pax) * (0.5f * width), deltay = (pby - pay) * (0.5f * width);
+    const double perpx = deltay, perpy = -deltax;
+    double vx[4], vy[4];  // top, right, bottom, left
+    if (pax < pbx) {
+        vx[0] = pax + perpx; vy[0] = pay + perpy;
+        vx[3] = pax - perpx; vy[3] = pay - perpy;
+        vx[1] = pbx + perpx; vy[1] = pby + perpy;
+        vx[2] = pbx - perpx; vy[2] = pby - perpy;
+    } else {
+        vx[0] = pax - perpx; vy[0] = pay - perpy;
+        vx[3] = pbx - perpx; vy[3] = pby - perpy;
+        vx[1] = pax + perpx; vy[1] = pay + perpy;
+        vx[2] = pbx + perpx; vy[2] = pby + perpy;
+    }
+    rot_scan_convert_quad(rb, vx, vy);
+}
+
+struct RotVertex {
+    double x, y, u, v;
+};
+
+PG_HD void rot_transform_trapezoid(RotBlit &rb, const RotVertex &topLeft, const RotVertex &bottomLeft, const RotVertex &topRight,
+                                   const RotVertex &bottomRight, double topY, double bottomY) {
+    long long fromY = pg_qround(topY);
+    if (fromY < 0) fromY = 0;
+    long long toY = pg_qround(bottomY);
+    if (toY > RES_H) toY = RES_H;
+    if (fromY >= toY)
+        return;
+    const double leftSlope = (bottomLeft.x - topLeft.x) / (bottomLeft.y - topLeft.y);
+    const double rightSlope = (bottomRight.x - topRight.x) / (bottomRight.y - topRight.y);
+    const long long dx_l = (long long)(leftSlope * 0x10000);
+    const long long dx_r = (long long)(rightSlope * 0x10000);
+    long long x_l = (long long)((topLeft.x + (0.5 + fromY - topLeft.y) * leftSlope + 0.5) * 0x10000);
+    long long x_r = (long long)((topRight.x + (0.5 + fromY - topRight.y) * rightSlope + 0.5) * 0x10000);
+    for (long long y = fromY; y < toY; ++y) {
+        long long fromX = x_l >> 16;
+        if (fromX < 0) fromX = 0;
+        long long toX = x_r >> 16;
+        if (toX > RES_W) toX = RES_W;
+        if (fromX < toX)
+            rot_span(rb, (int)fromX, (int)(toX - fromX), (int)y);
+        x_l += dx_l;
+        x_r += dx_r;
+    }
+}
+
+// qt_transform_image: three trapezoids + absolute 16.16 texel map
+PG_HD void rot_transform_image(RotBlit &rb, int sw, int sh, const double *r, const RotXform &m) {
+    RotVertex v[4];
+    v[0].u = v[3].u = 0;
+    v[0].v = v[1].v = 0;
+    v[1].u = v[2].u = sw;
+    v[3].v = v[2].v = sh;
+    v[0].x = v[3].x = r[0];
+    v[0].y = v[1].y = r[1];
+    v[1].x = v[2].x = r[0] + r[2];
+    v[3].y = v[2].y = r[1] + r[3];
+    for (int i = 0; i < 4; i++) {
+        double fx = v[i].x, fy = v[i].y;
+        v[i].x = m.m11 * fx + m.m21 * fy + m.dx;
+        v[i].y = m.m12 * fx + m.m22 * fy + m.dy;
+    }
+    int topmost = 0;
+    for (int i = 1; i < 4; ++i)
+        if (v[i].y < v[topmost].y)
+            topmost = i;
+    if (topmost == 1) {
+        RotVertex t = v[0];
+        v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = t;
+    } else if (topmost == 2) {
+        RotVertex t = v[0]; v[0] = v[2]; v[2] = t;
+        t = v[1]; v[1] = v[3]; v[3] = t;
+    } else if (topmost == 3) {
+        RotVertex t = v[3];
+        v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = t;
+    }
+    const double dx1 = v[1].x - v[0].x, dy1 = v[1].y - v[0].y;
+    const double dx2 = v[3].x - v[0].x, dy2 = v[3].y - v[0].y;
+    if (dx1 * dy2 - dx2 * dy1 > 0) {
+        RotVertex t = v[1]; v[1] = v[3]; v[3] = t;
+    }
+    const RotVertex u = {v[1].x - v[0].x, v[1].y - v[0].y, v[1].u - v[0].u, v[1].v - v[0].v};
+    const RotVertex w = {v[2].x - v[0].x, v[2].y - v[0].y, v[2].u - v[0].u, v[2].v - v[0].v};
+    const double det = u.x * w.y - u.y * w.x;
+    if (det == 0)
+        return;
+    const double invDet = 1.0 / det;
+    const double m11 = (u.u * w.y - u.y * w.u) * invDet;
+    const double m12 = (u.x * w.u - u.u * w.x) * invDet;
+    const double m21 = (u.v * w.y - u.y * w.v) * invDet;
+    const double m22 = (u.x * w.v - u.v * w.x) * invDet;
+    const double mdx = v[0].u - m11 * v[0].x - m12 * v[0].y;
+    const double mdy = v[0].v - m21 * v[0].x - m22 * v[0].y;
+    rb.absolute = 1;
+    rb.dudx = (int)(m11 * 0x10000);
+    rb.dvdx = (int)(m21 * 0x10000);
+    rb.dudy = (int)(m12 * 0x10000);
+    rb.dvdy = (int)(m22 * 0x10000);
+    rb.u0 = (int)pg_dceil((0.5 * m11 + 0.5 * m12 + mdx) * 0x10000) - 1;
+    rb.v0 = (int)pg_dceil((0.5 * m21 + 0.5 * m22 + mdy) * 0x10000) - 1;
+    if (v[1].y < v[3].y) {
+        rot_transform_trapezoid(rb, v[0], v[1], v[0], v[3], v[0].y, v[1].y);
+        rot_transform_trapezoid(rb, v[1], v[2], v[0], v[3], v[1].y, v[3].y);
+        rot_transform_trapezoid(rb, v[1], v[2], v[3], v[2], v[3].y, v[2].y);
+    } else {
+        rot_transform_trapezoid(rb, v[0], v[1], v[0], v[3], v[0].y, v[3].y);
+        rot_transform_trapezoid(rb, v[0], v[1], v[3], v[2], v[3].y, v[1].y);
+        rot_transform_trapezoid(rb, v[1], v[2], v[3], v[2], v[1].y, v[2].y);
+    }
+}
+
+// QRasterPaintEngine::drawImage under a rotating matrix: fills rb, returns false if nothing drawn
+PG_HD void rot_draw(RotBlit &rb, int sw, int sh, const double *r, const RotXform &m) {
+    for (int y = 0; y < RES_H; y++) rb.x1[y] = rb.x2[y] = 0;
+    rb.absolute = 0;
+    rb.dudx = rb.dvdx = rb.dudy = rb.dvdy = rb.u0 = rb.v0 = 0;
+    rb.m11 = rb.m12 = rb.m21 = rb.m22 = rb.dx = rb.dy = 0;
+    if (sw <= 0 || sh <= 0 || !(r[2] > 0) || !(r[3] > 0))
+        return;
+    double minx = 1e300, miny = 1e300, maxx = -1e300, maxy = -1e300;
+    for (int cidx = 0; cidx < 4; cidx++) {
+        const double fx = (cidx & 1) ? r[0] + r[2] : r[0], fy = (cidx & 2) ? r[1] + r[3] : r[1];
+        const double X = m.m11 * fx + m.m21 * fy + m.dx, Y = m.m12 * fx + m.m22 * fy + m.dy;
+        if (X < minx) minx = X;
+        if (X > maxx) maxx = X;
+        if (Y < miny) miny = Y;
+        if (Y > maxy) maxy = Y;
+    }
+    if (maxx - minx >= 16 && maxy - miny >= 16) {
+        rot_transform_image(rb, sw, sh, r, m);
+        return;
+    }
+    double c11 = m.m11, c12 = m.m12, c21 = m.m21, c22 = m.m22;
+    const double cdx = m.dx + r[0] * m.m11 + r[1] * m.m21;
+    const double cdy = m.dy + r[1] * m.m22 + r[0] * m.m12;
+    const double sx = r[2] / (double)sw, sy = r[3] / (double)sh;
+    c11 *= sx; c12 *= sx; c21 *= sy; c22 *= sy;
+    const double t = 1.0 / 65536;
+    const double pdx = t * c11 + t * c21 + cdx;
+    const double pdy = t * c12 + t * c22 + cdy;
+    const double det = c11 * c22 - c12 * c21;
+    if (det == 0)
+        return;
+    const double dinv = 1.0 / det;
+    rb.m11 = c22 * dinv;
+    rb.m12 = -c12 * dinv;
+    rb.m21 = -c21 * dinv;
+    rb.m22 = c11 * dinv;
+    rb.dx = (c21 * pdy - c22 * pdx) * dinv;
+    rb.dy = (c12 * pdx - c11 * pdy) * dinv;
+    rb.dudx = (int)(rb.m11 * 65536.0);  // fdx
+    rb.dvdx = (int)(rb.m12 * 65536.0);  // fdy
+    const double ly = (r[1] + (r[1] + r[3])) * 0.5f;
+    const double lx = (r[0] + r[0]) * 0.5f;
+    const double rx = ((r[0] + r[2]) + (r[0] + r[2])) * 0.5f;
+    const double ax = m.m11 * lx + m.m21 * ly + m.dx, ay = m.m12 * lx + m.m22 * ly + m.dy;
+    const double bx = m.m11 * rx + m.m21 * ly + m.dx, by = m.m12 * rx + m.m22 * ly + m.dy;
+    rot_rasterize_line(rb, ax, ay, bx, by, r[3] / r[2]);
 }
 
 // ---- rule F: opaque fillRect
@@ -182,7 +578,7 @@ PG_HD uint32_t blend_px(uint32_t dst, uint32_t src, int int_opacity) {
     return dst;
 }
 
-PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uint32_t *atlas) {
+PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uint32_t *atlas, const RotBlit *rots) {
     const uint32_t box = *reinterpret_cast<const uint32_t *>(&b);  // x1 | y1<<8 | w<<16 | h<<24
     const uint32_t dx = (uint32_t)px - (box & 0xffu);
     const uint32_t dy = (uint32_t)py - ((box >> 8) & 0xffu);
@@ -190,6 +586,32 @@ PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uin
         return dst;
     if (b.kind == BLIT_SOLID)
         return b.src;
+    if (b.kind == BLIT_ROTATED) {
+        const RotBlit &rb = rots[b.ix];
+        const int xs = rb.x1[py];
+        if (px < xs || px >= (int)rb.x2[py])
+            return dst;
+        long long tu, tv;
+        if (rb.absolute) {
+            tu = ((long long)px * rb.dudx + (long long)py * rb.dudy + rb.u0) >> 16;
+            tv = ((long long)px * rb.dvdx + (long long)py * rb.dvdy + rb.v0) >> 16;
+        } else {
+            const double cx = xs + 0.5, cy = py + 0.5;
+            int fx = (int)((rb.m21 * cy + rb.m11 * cx + rb.dx) * 65536.0);
+            int fy = (int)((rb.m22 * cy + rb.m12 * cx + rb.dy) * 65536.0);
+            fx = (int)((uint32_t)fx + (uint32_t)rb.dudx * (uint32_t)(px - xs));
+            fy = (int)((uint32_t)fy + (uint32_t)rb.dvdx * (uint32_t)(px - xs));
+            tu = fx >> 16;
+            tv = fy >> 16;
+        }
+        if (tu < 0) tu = 0;
+        if (tu > (long long)b.sw - 1) tu = (long long)b.sw - 1;
+        if (tv < 0) tv = 0;
+        if (tv > (long long)b.sh - 1) tv = (long long)b.sh - 1;
+        if (b.mirror)
+            tu = b.sw - 1 - tu;
+        return blend_px(dst, atlas[b.src + (uint32_t)tv * b.sw + (uint32_t)tu], b.opacity);
+    }
     uint32_t sx = (b.basex + (uint32_t)b.ix * dx) >> 16;
     uint32_t sy = (b.srcy + (uint32_t)b.iy * dy) >> 16;
     if (b.mirror)
@@ -242,7 +664,7 @@ struct Raster {
     }
 
     // draw_image (basic-abstract-game.cpp:877-913) for the un-rotated, un-tiled case
-    static PG_HD void make_sprite_blit(Ctx &c, const Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha) {
+    static PG_HD void make_sprite_blit(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha) {
         blit_clear(b);
         int img_type = G::image_for_type(c, base_type);
         if (img_type < 0)
@@ -272,9 +694,68 @@ struct Raster {
             io = (int)((double)alpha * 256);
         if (rotation == 0) {
             make_image_blit(b, rect[0], rect[1], rect[2], rect[3], sd, is_reflected, io, f.snap != 0);
-        } else {
-            c.h->err |= ERR_UNSUPPORTED;  // rotated sprites: not built yet
+            return;
         }
+        // basic-abstract-game.cpp:901-906: translate to the rect centre, rotate, draw the centred rect
+        RotXform m;
+        m.dx = rect[0] + rect[2] / 2;
+        m.dy = rect[1] + rect[3] / 2;
+        const double a = (double)(rotation * 180 / PI_F);
+        double sina = 0, cosa = 0;  // QTransform::rotate: exact at right angles
+        if (a == 90. || a == -270.)
+            sina = 1.;
+        else if (a == 270. || a == -90.)
+            sina = -1.;
+        else if (a == 180.)
+            cosa = -1.;
+        else {
+            const double rad = 0.017453292519943295769 * a;
+            sina = sin(rad);
+            cosa = cos(rad);
+        }
+        m.m11 = cosa; m.m12 = sina; m.m21 = -sina; m.m22 = cosa;
+        double r[4] = {-rect[2] / 2, -rect[3] / 2, rect[2], rect[3]};
+        if (pg_dfabs(m.m12) <= 1e-12 && pg_dfabs(m.m21) <= 1e-12) {
+            // QTransform::type() is fuzzy: +-180 degrees is a (mirroring) scale
+            make_image_blit(b, m.m11 * r[0] + m.dx, m.m22 * r[1] + m.dy, m.m11 * r[2], m.m22 * r[3], sd, is_reflected, io, f.snap != 0);
+            return;
+        }
+        int slot;
+#if defined(__CUDA_ARCH__)
+        slot = atomicAdd(&f.n_rot, 1);
+#else
+        slot = f.n_rot++;
+#endif
+        if (slot >= Frame::kMaxRot) {
+            c.h->err |= ERR_BLIT_OVERFLOW;
+            return;
+        }
+        RotBlit &rb = f.rot[slot];
+        rot_draw(rb, sd.w, sd.h, r, m);
+        int y0 = RES_H, y1 = -1, x0 = RES_W, x1 = 0;
+        for (int y = 0; y < RES_H; y++) {
+            if (rb.x2[y] > rb.x1[y]) {
+                if (y < y0) y0 = y;
+                y1 = y;
+                if (rb.x1[y] < x0) x0 = rb.x1[y];
+                if (rb.x2[y] > x1) x1 = rb.x2[y];
+            }
+        }
+        if (y1 < y0)
+            return;
+        b.x1 = (uint8_t)x0;
+        b.y1 = (uint8_t)y0;
+        b.w = (uint8_t)(x1 - x0);
+        b.h = (uint8_t)(y1 - y0 + 1);
+        b.kind = BLIT_ROTATED;
+        b.mirror = is_reflected ? 1 : 0;
+        b.opacity = (uint16_t)io;
+        b.ix = slot;
+        b.iy = 0;
+        b.basex = b.srcy = 0;
+        b.src = sd.off;
+        b.sw = sd.w;
+        b.sh = sd.h;
     }
 
     // prepare_for_drawing (basic-abstract-game.cpp:819-838). Writes the camera into the env
@@ -350,6 +831,7 @@ struct Raster {
             f.n_bg = 0;
             f.n_ent = 0;
             f.n_ent_below = 0;
+            f.n_rot = 0;
             if (overflow)
                 h.err |= ERR_BLIT_OVERFLOW;
             if (h.options.use_backgrounds)
@@ -392,7 +874,7 @@ struct Raster {
     }
 
     // One blit for entity `ei`, or kind NONE when it is not drawn / off screen.
-    static PG_HD void entity_blit(Ctx &c, const Frame &f, int ei, Blit &b) {
+    static PG_HD void entity_blit(Ctx &c, Frame &f, int ei, Blit &b) {
         blit_clear(b);
         if (!G::should_draw_entity(c, ei))
             return;
@@ -518,7 +1000,7 @@ struct Raster {
     // ---- phase D: the gather. Returns 0xFFRRGGBB (Format_RGB32).
     static PG_HD uint32_t shade_pixel(const Frame &f, int px, int py, const uint32_t *atlas) {
         uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
-        for (int i = 0; i < f.n_bg; i++) dst = apply_blit(f.bg[i], px, py, dst, atlas);
+        for (int i = 0; i < f.n_bg; i++) dst = apply_blit(f.bg[i], px, py, dst, atlas, f.rot);
         uint64_t above[Frame::kEntWords];
         const int nb = f.n_ent_below;
         for (int w = 0; w < Frame::kEntWords; w++) {
@@ -531,7 +1013,7 @@ struct Raster {
             while (mb) {
                 const int i = ctz64(mb);
                 mb &= mb - 1;
-                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas);
+                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
             }
         }
         const int clo = f.col_lo[px], chi = f.col_hi[px];
@@ -539,17 +1021,17 @@ struct Raster {
         if (clo != 255 && rlo != 255) {
             for (int ci = clo; ci <= chi; ci++)
                 for (int cj = rlo; cj <= rhi; cj++)
-                    dst = apply_blit(f.cells[ci * f.ny + cj], px, py, dst, atlas);
+                    dst = apply_blit(f.cells[ci * f.ny + cj], px, py, dst, atlas, f.rot);
         }
         for (int w = 0; w < Frame::kEntWords; w++) {
             uint64_t ma = above[w];
             while (ma) {
                 const int i = ctz64(ma);
                 ma &= ma - 1;
-                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas);
+                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
             }
         }
-        for (int i = 0; i < f.n_overlay; i++) dst = apply_blit(f.overlay[i], px, py, dst, atlas);
+        for (int i = 0; i < f.n_overlay; i++) dst = apply_blit(f.overlay[i], px, py, dst, atlas, f.rot);
         return dst;
     }
 };

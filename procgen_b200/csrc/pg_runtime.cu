@@ -126,10 +126,10 @@ std::vector<std::string> split(std::string s, const std::string &delim) {
 #define PG_LOGIC_MIN_BLOCKS 24
 #endif
 #ifndef PG_STEP_CHUNKS
-#define PG_STEP_CHUNKS 4
+#define PG_STEP_CHUNKS 8
 #endif
 #ifndef PG_AUX_STREAMS
-#define PG_AUX_STREAMS 2
+#define PG_AUX_STREAMS 8
 #endif
 constexpr int kLogicThreads = 32 * PG_LOGIC_WARPS;  // one warp = one env; few warps per CTA so a finished
 constexpr int kLogicEnvsPerBlock = PG_LOGIC_WARPS;  // env frees its slot without waiting on many siblings

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle.ref_env import RefVecEnv, mt19937_actions  # noqa: E402
 
-CASES = [("coinrun", "easy", 8, 96), ("coinrun", "hard", 8, 96), ("bigfish", "hard", 8, 96), ("maze", "hard", 8, 96)]
+CASES = [("coinrun", "easy", 8, 96), ("coinrun", "hard", 8, 96), ("bigfish", "hard", 8, 96), ("maze", "hard", 8, 96), ("heist", "hard", 8, 96)]
 
 
 def main():

@@ -92,3 +92,30 @@ def test_raster_restatement_matches_real_qt6(ref_lib, asset_pack):
             assert np.array_equal(oa["rgb"], ob["rgb"]), f"{name} step {t}: restatement != Qt 6.6.3"
         a.close()
         b.close()
+
+
+def test_rotated_raster_restatement_close_to_real_qt6(ref_lib, asset_pack):
+    """Rotated sprites (heist): the restatement follows Qt's two transformed-image paths. Texels are
+    exact; coverage of small quads differs from Qt 6.6.3 only at exact 45-degree headings (26.6
+    scan-converter ties). Budget: <= 1e-5 of all pixels (measured 3e-6)."""
+    from oracle import build_ref, qt6_support
+    from oracle.ref_env import REF_LIB_QT6
+
+    if not qt6_support.available() or not os.path.exists(REF_LIB_QT6):
+        pytest.skip("Qt 6 backend not available")
+    n, steps = 8, 200
+    a = RefVecEnv(n, "heist", distribution_mode="hard", num_levels=0, rand_seed=3)
+    b = RefVecEnv(n, "heist", distribution_mode="hard", num_levels=0, rand_seed=3, lib_path=REF_LIB_QT6)
+    acts = mt19937_actions(0, n, steps)
+    bad = tot = 0
+    for t in range(steps):
+        a.act(acts[t])
+        b.act(acts[t])
+        _, oa, _ = a.observe()
+        _, ob, _ = b.observe()
+        d = (oa["rgb"] != ob["rgb"]).any(-1)
+        bad += int(d.sum())
+        tot += d.size
+    a.close()
+    b.close()
+    assert bad <= 1e-5 * tot, f"{bad} of {tot} pixels differ from Qt 6.6.3"
