@@ -57,6 +57,34 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[2] = {"misc_assets/cheese.png"};
         T[0] = {"kenney/Enemies/mouse_move.png"};
         break;
+    case GAME_LEAPER:  // leaper.cpp:42-69
+        g.bg_group = "topdown_backgrounds";
+        T[2] = {"misc_assets/roadTile6b.png"};
+        T[3] = {"misc_assets/terrainTile6.png"};
+        T[4] = {"misc_assets/car_yellow_5.png", "misc_assets/car_black_1.png", "misc_assets/car_blue_2.png",
+                "misc_assets/car_green_3.png", "misc_assets/car_red_4.png"};
+        T[1] = {"misc_assets/elementWood044.png"};
+        T[0] = {"misc_assets/frog1.png", "misc_assets/frog2.png", "misc_assets/frog4.png", "misc_assets/frog6.png",
+                "misc_assets/frog7.png"};
+        T[5] = {"misc_assets/finish2.png"};
+        break;
+    case GAME_PLUNDER:  // plunder.cpp:46-64
+        g.bg_group = "water_surface_backgrounds";
+        T[7] = {"misc_assets/ship_1.png", "misc_assets/ship_2.png", "misc_assets/ship_3.png", "misc_assets/ship_4.png",
+                "misc_assets/ship_5.png", "misc_assets/ship_6.png"};
+        T[1] = {"misc_assets/cannonBall.png"};
+        T[6] = {"misc_assets/panel_wood.png"};
+        T[3] = {"misc_assets/target_red2.png"};
+        break;
+    case GAME_MINER:  // miner.cpp:38-56
+        g.bg_group = "platform_backgrounds";
+        T[0] = {"misc_assets/robot_greenDrive1.png"};
+        T[1] = {"misc_assets/elementStone007.png"};
+        T[2] = {"misc_assets/gemBlue.png"};
+        T[6] = {"misc_assets/window.png"};
+        T[9] = {"misc_assets/dirt.png"};
+        T[10] = {"misc_assets/tile_bricksGrey.png"};
+        break;
     default:
         throw std::runtime_error("procgen_b200: game id " + std::to_string(game_id) + " has no asset table yet");
     }

@@ -186,6 +186,45 @@ struct ScanDownIter {
     }
 };
 
+// Ascending twin of ScanDownIter: smallest i in [from, n) with pred(i), keeping the rest of the
+// chunk's ballot until restart_from() is called.
+struct ScanUpIter {
+    int next_base, cur_base, n;
+    unsigned mask;
+    PG_HD ScanUpIter(int from, int n_) : next_base(from), cur_base(from), n(n_), mask(0) {}
+    template <class F>
+    PG_HD int next(F pred) {
+#if defined(__CUDA_ARCH__)
+        const int lane = (int)(threadIdx.x & 31u);
+        while (true) {
+            if (mask) {
+                const int b = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                return cur_base + b;
+            }
+            if (next_base >= n)
+                return -1;
+            cur_base = next_base;
+            next_base += 32;
+            const int i = cur_base + lane;
+            const bool hit = (i < n) && pred(i);
+            mask = __ballot_sync(0xffffffffu, hit);
+        }
+#else
+        while (next_base < n) {
+            const int i = next_base++;
+            if (pred(i))
+                return i;
+        }
+        return -1;
+#endif
+    }
+    PG_HD void restart_from(int i) {
+        mask = 0;
+        next_base = i;
+    }
+};
+
 // pg_warp_for(n, f): f(i) for every i in [0, n); iterations must be independent (disjoint writes).
 // On the device the warp's lanes stride over i and a __syncwarp() publishes the writes before the
 // lanes go back to uniform execution.

@@ -758,6 +758,25 @@ struct Raster {
         b.sh = sd.h;
     }
 
+    // draw_image's inner part for an already-resolved image type and already-adjusted rect
+    static PG_HD void make_sprite_blit_noadjust(Ctx &c, Frame &f, Blit &b, double *rect, bool is_reflected, int img_type, int theme, float alpha) {
+        blit_clear(b);
+        if (theme < 0 || theme >= MAX_IMAGE_THEMES) {
+            c.h->err |= ERR_FASSERT;
+            return;
+        }
+        int masked_theme = (c.h->options.restrict_themes && !G::should_preserve_type_themes(c, img_type)) ? 0 : theme;
+        SpriteDesc sd = c.assets->sprites[img_type + masked_theme * MAX_ASSETS];
+        if (sd.w == 0) {
+            c.h->err |= ERR_UNSUPPORTED;
+            return;
+        }
+        int io = 256;
+        if (alpha != 1)
+            io = (int)((double)alpha * 256);
+        make_image_blit(b, rect[0], rect[1], rect[2], rect[3], sd, is_reflected, io, f.snap != 0);
+    }
+
     // prepare_for_drawing (basic-abstract-game.cpp:819-838). Writes the camera into the env
     // header (those fields are part of the serialized state, :1202-1220). Logic thread.
     static PG_HD void prepare_camera(Ctx &c) {
@@ -873,25 +892,92 @@ struct Raster {
         hi = (uint8_t)hgh;
     }
 
-    // One blit for entity `ei`, or kind NONE when it is not drawn / off screen.
-    static PG_HD void entity_blit(Ctx &c, Frame &f, int ei, Blit &b) {
-        blit_clear(b);
+    // tile_image (basic-abstract-game.cpp:840-869): number of tiles an entity's sprite is repeated
+    // over (0 = plain single draw) and the rect of tile i. Float/double mix as in the reference.
+    static PG_HD int tile_count(const double *rect, float tile_ratio) {
+        if (tile_ratio == 0)
+            return 0;
+        int num_tiles;
+        if (tile_ratio < 0) {
+            tile_ratio = -1 * tile_ratio;
+            num_tiles = (int)(rect[3] / (rect[2] * (double)tile_ratio));
+        } else {
+            num_tiles = (int)(rect[2] / (rect[3] * (double)tile_ratio));
+        }
+        if (num_tiles < 1)
+            num_tiles = 1;
+        return num_tiles;
+    }
+    static PG_HD void tile_rect(const double *rect, float tile_ratio, int num_tiles, int i, double *out) {
+        if (tile_ratio < 0) {
+            float tile_height = (float)(rect[3] / num_tiles);
+            float tile_width = (float)rect[2];
+            out[0] = rect[0];
+            out[1] = rect[1] + (double)(tile_height * i);
+            out[2] = (double)tile_width;
+            out[3] = (double)tile_height;
+        } else {
+            float tile_width = (float)(rect[2] / num_tiles);
+            float tile_height = (float)rect[3];
+            out[0] = rect[0] + (double)(tile_width * i);
+            out[1] = rect[1];
+            out[2] = (double)tile_width;
+            out[3] = (double)tile_height;
+        }
+    }
+
+    // Blits of entity `ei`: 0 (not drawn / off screen), 1 (normal) or one per tile. `emit(j, blit)`
+    // is called for j in [0, count) when `store` is set; returns count.
+    template <class Emit>
+    static PG_HD int entity_blits(Ctx &c, Frame &f, int ei, bool store, Blit &single, Emit emit) {
+        blit_clear(single);
         if (!G::should_draw_entity(c, ei))
-            return;
+            return 0;
         const Entity &o = c.ents[ei];
         double r[4];
         object_rect(f.cam, o, r);
         float tile_ratio = G::get_tile_aspect_ratio(c, ei);
-        if (tile_ratio != 0) {
-            c.h->err |= ERR_UNSUPPORTED;  // tiled entities: not built yet
-            return;
+        if (tile_ratio != 0 && o.rotation == 0) {
+            // draw_image: the adjusted rect is tiled (adjustment first, basic-abstract-game.cpp:890-900)
+            int img_type = G::image_for_type(c, o.image_type);
+            if (img_type < 0 || img_type >= USE_ASSET_THRESHOLD || c.h->options.use_monochrome_assets) {
+                if (store)
+                    make_sprite_blit(c, f, single, r, 0, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
+                else
+                    make_sprite_blit(c, f, single, r, 0, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
+                if (single.kind == BLIT_NONE)
+                    return 0;
+                if (store)
+                    emit(0, single);
+                return 1;
+            }
+            double adj[4];
+            if (G::get_adjusted_image_rect(c, img_type, adj))
+                adjust_rect(r, adj);
+            const int nt = tile_count(r, tile_ratio);
+            if (store) {
+                for (int i = 0; i < nt; i++) {
+                    double tr[4];
+                    tile_rect(r, tile_ratio, nt, i, tr);
+                    Blit b;
+                    make_sprite_blit_noadjust(c, f, b, tr, o.is_reflected != 0, img_type, o.image_theme, o.alpha);
+                    emit(i, b);
+                }
+            }
+            return nt;
         }
-        make_sprite_blit(c, f, b, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
+        make_sprite_blit(c, f, single, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
+        if (single.kind == BLIT_NONE)
+            return 0;
+        if (store)
+            emit(0, single);
+        return 1;
     }
 
-    // Entities -> visible blits in draw order (draw_entities z=-1 / 0 / 1, basic-abstract-game.cpp:
-    // 1059-1066), culled. `lane`/`gsize`: the cooperating group (a full warp on the device, 1 in the
-    // host harness). Stable compaction uses the group's ballot.
+    // Entities -> blits in draw order (draw_entities z=-1 / 0 / 1, basic-abstract-game.cpp:1059-1066),
+    // culled. `lane`/`gsize`: the cooperating group (a full warp on the device, 1 in the host
+    // harness). Each lane owns one entity per round; a warp prefix sum of the per-entity blit counts
+    // keeps the list in draw order.
     static PG_HD void build_entity_blits(Ctx &c, Frame &f, int lane, int gsize) {
         const int n = c.h->n_ents;
         int count = 0;
@@ -899,24 +985,38 @@ struct Raster {
         for (int z = -1; z <= 1; z++) {
             for (int base = 0; base < n; base += gsize) {
                 const int ei = base + lane;
-                Blit b;
-                blit_clear(b);
-                if (ei < n && c.ents[ei].render_z == z)
-                    entity_blit(c, f, ei, b);
-                const bool keep = b.kind != BLIT_NONE;
+                Blit single;
+                blit_clear(single);
+                int mine = 0;
+                const bool active = ei < n && c.ents[ei].render_z == z;
+                bool tiled = false;
+                if (active) {
+                    tiled = G::get_tile_aspect_ratio(c, ei) != 0 && c.ents[ei].rotation == 0;
+                    mine = entity_blits(c, f, ei, false, single, [](int, const Blit &) {});
+                }
+                int pos = count;
+                int total = mine;
 #if defined(__CUDA_ARCH__)
-                const unsigned mask = __ballot_sync(0xffffffffu, keep);
-                const int pos = count + __popc(mask & ((1u << lane) - 1u));
-                const int total = __popc(mask);
-#else
-                const int pos = count;
-                const int total = keep ? 1 : 0;
+                int incl = mine;
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d)
+                        incl += t;
+                }
+                pos = count + incl - mine;
+                total = __shfl_sync(0xffffffffu, incl, 31);
 #endif
-                if (keep) {
-                    if (pos < Frame::kMaxEntBlits)
-                        f.ents[pos] = b;
-                    else
+                if (mine > 0) {
+                    if (pos + mine <= Frame::kMaxEntBlits) {
+                        if (!tiled) {
+                            f.ents[pos] = single;
+                        } else {
+                            Blit *dst = f.ents + pos;
+                            entity_blits(c, f, ei, true, single, [=](int j, const Blit &b) { dst[j] = b; });
+                        }
+                    } else {
                         c.h->err |= ERR_BLIT_OVERFLOW;
+                    }
                 }
                 count += total;
             }

@@ -24,7 +24,10 @@
 #include "games/bigfish.cuh"
 #include "games/coinrun.cuh"
 #include "games/heist.cuh"
+#include "games/leaper.cuh"
 #include "games/maze.cuh"
+#include "games/miner.cuh"
+#include "games/plunder.cuh"
 
 #ifndef PG_HOSTSIM
 #include <cuda_runtime.h>
@@ -243,7 +246,10 @@ const GameVTable *find_game(const std::string &name) {
         make_vtable<BigFish>(GAME_BIGFISH),
         make_vtable<CoinRun>(GAME_COINRUN),
         make_vtable<HeistGame>(GAME_HEIST),
+        make_vtable<LeaperGame>(GAME_LEAPER),
         make_vtable<MazeGame>(GAME_MAZE),
+        make_vtable<MinerGame>(GAME_MINER),
+        make_vtable<PlunderGame>(GAME_PLUNDER),
     };
     for (const auto &g : table)
         if (name == g.name)
