@@ -57,6 +57,33 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[2] = {"misc_assets/cheese.png"};
         T[0] = {"kenney/Enemies/mouse_move.png"};
         break;
+    case GAME_CHASER:  // chaser.cpp:51-75
+        g.bg_group = "topdown_simple_backgrounds";
+        T[0] = {"misc_assets/enemyFloating_1b.png"};
+        T[6] = {"misc_assets/enemyFlying_1.png"};
+        T[7] = {"misc_assets/enemyFlying_2.png"};
+        T[8] = {"misc_assets/enemyFlying_3.png"};
+        T[2] = {"misc_assets/yellowCrystal.png"};
+        T[3] = {"misc_assets/enemyWalking_1b.png"};
+        T[4] = {"misc_assets/enemySpikey_1b.png"};
+        T[5] = {"misc_assets/tileStone_slope.png"};
+        break;
+    case GAME_CLIMBER: {  // climber.cpp:47-89
+        g.bg_group = "platform_backgrounds";
+        const char *cols[4] = {"Blue", "Green", "Grey", "Red"};
+        for (auto col : cols) {
+            T[0].push_back(std::string("platformer/player") + col + "_stand.png");
+            T[9].push_back(std::string("platformer/player") + col + "_walk4.png");
+            T[12].push_back(std::string("platformer/player") + col + "_walk1.png");
+            T[13].push_back(std::string("platformer/player") + col + "_walk2.png");
+        }
+        T[16] = {"platformer/tileBlue_05.png", "platformer/tileGreen_05.png", "platformer/tileYellow_06.png", "platformer/tileBrown_06.png"};
+        T[15] = {"platformer/tileBlue_08.png", "platformer/tileGreen_08.png", "platformer/tileYellow_09.png", "platformer/tileBrown_09.png"};
+        T[6] = {"platformer/enemySwimming_1.png"};
+        T[7] = {"platformer/enemySwimming_2.png"};
+        T[1] = {"platformer/yellowCrystal.png"};
+        break;
+    }
     case GAME_LEAPER:  // leaper.cpp:42-69
         g.bg_group = "topdown_backgrounds";
         T[2] = {"misc_assets/roadTile6b.png"};
@@ -67,6 +94,19 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[0] = {"misc_assets/frog1.png", "misc_assets/frog2.png", "misc_assets/frog4.png", "misc_assets/frog6.png",
                 "misc_assets/frog7.png"};
         T[5] = {"misc_assets/finish2.png"};
+        break;
+    case GAME_NINJA:  // ninja.cpp:46-75
+        g.bg_group = "platform_backgrounds";
+        T[20] = {"misc_assets/tile_bricksGrey.png", "misc_assets/tile_bricksGrown.png", "misc_assets/tile_bricksRed.png"};
+        T[1] = {"platformer/shroom1.png", "platformer/shroom2.png", "platformer/shroom3.png", "platformer/shroom4.png",
+                "platformer/shroom5.png", "platformer/shroom6.png"};
+        T[0] = {"platformer/zombie_idle.png"};
+        T[9] = {"platformer/zombie_jump.png"};
+        T[12] = {"platformer/zombie_walk1.png"};
+        T[13] = {"platformer/zombie_walk2.png"};
+        T[6] = {"misc_assets/bomb.png"};
+        T[7] = {"misc_assets/saw.png"};
+        T[14] = {"misc_assets/bomb.png"};
         break;
     case GAME_PLUNDER:  // plunder.cpp:46-64
         g.bg_group = "water_surface_backgrounds";

@@ -22,11 +22,14 @@
 #include "pg_asset_tables.h"
 #include "pg_kernels.cuh"
 #include "games/bigfish.cuh"
+#include "games/chaser.cuh"
+#include "games/climber.cuh"
 #include "games/coinrun.cuh"
 #include "games/heist.cuh"
 #include "games/leaper.cuh"
 #include "games/maze.cuh"
 #include "games/miner.cuh"
+#include "games/ninja.cuh"
 #include "games/plunder.cuh"
 
 #ifndef PG_HOSTSIM
@@ -244,11 +247,14 @@ GameVTable make_vtable(int id) {
 const GameVTable *find_game(const std::string &name) {
     static const GameVTable table[] = {
         make_vtable<BigFish>(GAME_BIGFISH),
+        make_vtable<ChaserGame>(GAME_CHASER),
+        make_vtable<Climber>(GAME_CLIMBER),
         make_vtable<CoinRun>(GAME_COINRUN),
         make_vtable<HeistGame>(GAME_HEIST),
         make_vtable<LeaperGame>(GAME_LEAPER),
         make_vtable<MazeGame>(GAME_MAZE),
         make_vtable<MinerGame>(GAME_MINER),
+        make_vtable<Ninja>(GAME_NINJA),
         make_vtable<PlunderGame>(GAME_PLUNDER),
     };
     for (const auto &g : table)
