@@ -43,6 +43,21 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[0] = {"misc_assets/fishTile_072.png"};
         T[2] = {"misc_assets/fishTile_074.png", "misc_assets/fishTile_078.png", "misc_assets/fishTile_080.png"};
         break;
+    case GAME_FRUITBOT: {  // fruitbot.cpp:47-81
+        g.bg_group = "topdown_backgrounds";
+        T[0] = {"misc_assets/robot_3Dblue.png"};
+        T[1] = {"misc_assets/tileStone_slope.png"};
+        T[2] = {"misc_assets/tileStone_slope.png"};
+        T[3] = {"misc_assets/keyRed2.png"};
+        for (int i = 1; i <= 6; i++) {
+            T[4].push_back("misc_assets/food" + std::to_string(i) + ".png");
+            T[7].push_back("misc_assets/fruit" + std::to_string(i) + ".png");
+        }
+        T[10] = {"misc_assets/fenceYellow.png"};
+        T[11] = {"misc_assets/lockRed2.png"};
+        T[12] = {"misc_assets/present1.png", "misc_assets/present2.png", "misc_assets/present3.png"};
+        break;
+    }
     case GAME_HEIST:  // heist.cpp:36-60
         g.bg_group = "topdown_backgrounds";
         T[51] = {"kenney/Ground/Dirt/dirtCenter.png"};

@@ -954,6 +954,9 @@ struct Raster {
             double adj[4];
             if (G::get_adjusted_image_rect(c, img_type, adj))
                 adjust_rect(r, adj);
+            // entirely off screen (with a one pixel guard band for the rounding rules): no tiles
+            if (r[0] + r[2] < -1 || r[1] + r[3] < -1 || r[0] > RES_W + 1 || r[1] > RES_H + 1)
+                return 0;
             const int nt = tile_count(r, tile_ratio);
             if (store) {
                 for (int i = 0; i < nt; i++) {
@@ -1147,7 +1150,22 @@ struct DrawDefaults {
         Raster<G, Frame>::screen_rect(f.cam, 0, (float)h.main_height, (float)h.main_width, (float)h.main_height, 0, main_rect);
         SpriteDesc bg = c.assets->backgrounds[h.background_index];
         if (h.bg_tile_ratio < 0) {
-            h.err |= ERR_UNSUPPORTED;  // vertical tiling (fruitbot): not built yet
+            // tile_image(p, background, main_rect, bg_tile_ratio), basic-abstract-game.cpp:990-991
+            const int nt = Raster<G, Frame>::tile_count(main_rect, h.bg_tile_ratio);
+            int n = 0;
+            for (int i = 0; i < nt; i++) {
+                double tr[4];
+                Raster<G, Frame>::tile_rect(main_rect, h.bg_tile_ratio, nt, i, tr);
+                Blit b;
+                make_image_blit(b, tr[0], tr[1], tr[2], tr[3], bg, false, 256, f.snap != 0);
+                if (b.kind == BLIT_NONE)
+                    continue;  // tile entirely off screen
+                if (n < MAX_BG_BLITS)
+                    f.bg[n++] = b;
+                else
+                    h.err |= ERR_BLIT_OVERFLOW;
+            }
+            f.n_bg = n;
             return;
         }
         float bgw = bg.w;

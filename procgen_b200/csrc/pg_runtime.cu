@@ -25,6 +25,7 @@
 #include "games/chaser.cuh"
 #include "games/climber.cuh"
 #include "games/coinrun.cuh"
+#include "games/fruitbot.cuh"
 #include "games/heist.cuh"
 #include "games/leaper.cuh"
 #include "games/maze.cuh"
@@ -250,6 +251,7 @@ const GameVTable *find_game(const std::string &name) {
         make_vtable<ChaserGame>(GAME_CHASER),
         make_vtable<Climber>(GAME_CLIMBER),
         make_vtable<CoinRun>(GAME_COINRUN),
+        make_vtable<FruitBotGame>(GAME_FRUITBOT),
         make_vtable<HeistGame>(GAME_HEIST),
         make_vtable<LeaperGame>(GAME_LEAPER),
         make_vtable<MazeGame>(GAME_MAZE),

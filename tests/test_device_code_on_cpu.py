@@ -17,6 +17,18 @@ CASES = [
     ("heist", "easy", 16, 400),     # rotated sprites (agent heading, key ring)
     ("heist", "hard", 16, 500),
     ("heist", "memory", 8, 300),
+    ("miner", "hard", 16, 400),
+    ("miner", "memory", 8, 300),
+    ("leaper", "hard", 16, 400),    # tiled finish line, rotated cars/frog
+    ("leaper", "extreme", 8, 300),
+    ("plunder", "hard", 16, 500),   # HUD overlay bars, bullets (collides_with_entities)
+    ("chaser", "hard", 16, 400),    # maze without dead ends, solid-colour orbs
+    ("chaser", "extreme", 8, 300),
+    ("climber", "hard", 16, 400),   # custom camera (choose_center)
+    ("ninja", "hard", 16, 500),     # bombs/explosions, throwing stars (sin/cos), charge bar
+    ("ninja", "easy", 16, 300),
+    ("fruitbot", "hard", 16, 400),  # vertically tiled background, tiled barriers and doors
+    ("fruitbot", "easy", 16, 300),
 ]
 
 

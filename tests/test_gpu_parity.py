@@ -22,6 +22,13 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     ("maze", "easy", 32, 500),
     ("heist", "hard", 64, 800),      # configs[3]; exercises the rotated-sprite raster paths
     ("heist", "easy", 32, 500),
+    ("miner", "hard", 32, 600),
+    ("leaper", "hard", 32, 600),
+    ("plunder", "hard", 32, 800),
+    ("chaser", "hard", 32, 600),
+    ("climber", "hard", 32, 600),
+    ("ninja", "hard", 32, 800),
+    ("fruitbot", "hard", 32, 600),
 ])
 def test_libenv_host_buffers_bit_exact(ref_lib, product_lib, name, mode, n, steps):
     ref, dut = make_pair(product_lib, n, name, distribution_mode=mode, num_levels=200, start_level=0, rand_seed=0)
