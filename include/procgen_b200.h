@@ -169,6 +169,10 @@ LIBENV_API uint32_t pgb200_get_errors(libenv_env *handle, uint32_t *host_out);
  * Returns -1 when timing was not enabled. */
 LIBENV_API int pgb200_debug_cycles(libenv_env *handle, uint32_t *host_out);
 
+/* Debug/inspection aid: copies env `env`'s header (512 B, layout csrc/pg_state.cuh EnvHdr) and up to
+ * max_ents entity records (128 B each, csrc/pg_state.cuh Entity) to host memory; returns n_ents. */
+LIBENV_API int pgb200_debug_read_env(libenv_env *handle, int env, void *hdr_out, void *ents_out, int max_ents);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 LIBENV_API int64_t pgb200_kernel_launches(libenv_env *handle);
 

@@ -152,12 +152,10 @@ struct HeistGame : Defaults<HeistGame>, DrawDefaults<HeistGame> {
             E::match_aspect_ratio(c, ent);
         }
     }
-    // heist.cpp:206-210; Entity::face_direction entity.cpp:84-88 (atan2 is the double overload)
+    // heist.cpp:206-210
     static PG_HD void game_step(Ctx &c) {
         E::basic_game_step(c);
-        float dx = c.h->action_vx, dy = c.h->action_vy;
-        if (dx != 0 || dy != 0)
-            agent_of(c).rotation = (float)(-1 * atan2((double)dy, (double)dx) + (double)0.0f);
+        entity_face_direction(agent_of(c), c.h->action_vx, c.h->action_vy);
     }
 };
 

@@ -72,6 +72,17 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[2] = {"misc_assets/cheese.png"};
         T[0] = {"kenney/Enemies/mouse_move.png"};
         break;
+    case GAME_CAVEFLYER:  // caveflyer.cpp:36-54
+        g.bg_group = "space_backgrounds";
+        T[1] = {"misc_assets/ufoGreen2.png"};
+        T[2] = {"misc_assets/meteorBrown_big1.png"};
+        T[3] = {"misc_assets/ufoRed2.png"};
+        T[4] = {"misc_assets/laserBlue02.png"};
+        T[5] = {"misc_assets/enemyShipBlue4.png"};
+        T[0] = {"misc_assets/playerShip1_red.png"};
+        T[8] = {"misc_assets/groundA.png"};
+        T[9] = {"misc_assets/towerDefense_tile295.png"};
+        break;
     case GAME_CHASER:  // chaser.cpp:51-75
         g.bg_group = "topdown_simple_backgrounds";
         T[0] = {"misc_assets/enemyFloating_1b.png"};

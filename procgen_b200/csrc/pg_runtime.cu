@@ -22,6 +22,7 @@
 #include "pg_asset_tables.h"
 #include "pg_kernels.cuh"
 #include "games/bigfish.cuh"
+#include "games/caveflyer.cuh"
 #include "games/chaser.cuh"
 #include "games/climber.cuh"
 #include "games/coinrun.cuh"
@@ -248,6 +249,7 @@ GameVTable make_vtable(int id) {
 const GameVTable *find_game(const std::string &name) {
     static const GameVTable table[] = {
         make_vtable<BigFish>(GAME_BIGFISH),
+        make_vtable<CaveFlyerGame>(GAME_CAVEFLYER),
         make_vtable<ChaserGame>(GAME_CHASER),
         make_vtable<Climber>(GAME_CLIMBER),
         make_vtable<CoinRun>(GAME_COINRUN),
@@ -955,6 +957,30 @@ int pgb200_debug_cycles(libenv_env *handle, uint32_t *host_out) {
     CUDA_CHECK(cudaMemcpy(host_out, v->base.dbg_cycles, (size_t)v->num_envs * 4, cudaMemcpyDeviceToHost));
 #endif
     return 0;
+}
+
+int pgb200_debug_read_env(libenv_env *handle, int env, void *hdr_out, void *ents_out, int max_ents) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+    EnvHdr hdr;
+    const KParams &p = v->base;
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMemcpy(&hdr, p.hdr + env, sizeof(EnvHdr), cudaMemcpyDeviceToHost));
+#else
+    memcpy(&hdr, p.hdr + env, sizeof(EnvHdr));
+#endif
+    if (hdr_out)
+        memcpy(hdr_out, &hdr, sizeof(EnvHdr));
+    int n = hdr.n_ents < max_ents ? hdr.n_ents : max_ents;
+    if (ents_out && n > 0) {
+#ifndef PG_HOSTSIM
+        CUDA_CHECK(cudaMemcpy(ents_out, p.ents + (size_t)env * p.ent_stride, (size_t)n * sizeof(Entity), cudaMemcpyDeviceToHost));
+#else
+        memcpy(ents_out, p.ents + (size_t)env * p.ent_stride, (size_t)n * sizeof(Entity));
+#endif
+    }
+    return hdr.n_ents;
 }
 
 int64_t pgb200_kernel_launches(libenv_env *handle) { return ((VecEnv *)handle)->launches; }

@@ -46,7 +46,7 @@ class DeviceBuffers(C.Structure):
 
 EXPORTS = ["libenv_version", "libenv_make", "libenv_get_tensortypes", "libenv_set_buffers", "libenv_observe",
            "libenv_act", "libenv_close", "pgb200_get_device_buffers", "pgb200_set_stream", "pgb200_act_device",
-           "pgb200_sync", "pgb200_get_errors", "pgb200_debug_cycles", "pgb200_kernel_launches", "pgb200_is_device_build"]
+           "pgb200_sync", "pgb200_get_errors", "pgb200_debug_cycles", "pgb200_debug_read_env", "pgb200_kernel_launches", "pgb200_is_device_build"]
 
 _lib = None
 
@@ -70,6 +70,8 @@ def bind(lib):
     lib.pgb200_get_errors.restype = C.c_uint32
     lib.pgb200_debug_cycles.argtypes = [C.c_void_p, C.c_void_p]
     lib.pgb200_debug_cycles.restype = C.c_int
+    lib.pgb200_debug_read_env.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.pgb200_debug_read_env.restype = C.c_int
     lib.pgb200_kernel_launches.argtypes = [C.c_void_p]
     lib.pgb200_kernel_launches.restype = C.c_int64
     lib.pgb200_is_device_build.restype = C.c_int
