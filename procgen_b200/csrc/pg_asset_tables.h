@@ -72,6 +72,19 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[2] = {"misc_assets/cheese.png"};
         T[0] = {"kenney/Enemies/mouse_move.png"};
         break;
+    case GAME_BOSSFIGHT:  // bossfight.cpp:77-109
+        g.bg_group = "space_backgrounds";
+        T[0] = {"misc_assets/playerShip1_blue.png", "misc_assets/playerShip1_green.png", "misc_assets/playerShip2_orange.png",
+                "misc_assets/playerShip3_red.png"};
+        T[2] = {"misc_assets/enemyShipBlack1.png", "misc_assets/enemyShipBlue2.png", "misc_assets/enemyShipGreen3.png",
+                "misc_assets/enemyShipRed4.png"};
+        T[4] = {"misc_assets/laserGreen14.png", "misc_assets/laserRed11.png", "misc_assets/laserBlue09.png"};
+        T[1] = {"misc_assets/laserGreen14.png", "misc_assets/laserRed11.png", "misc_assets/laserBlue09.png"};
+        T[3] = {"misc_assets/shield2.png"};
+        T[7] = {"misc_assets/spaceMeteors_001.png", "misc_assets/spaceMeteors_002.png", "misc_assets/spaceMeteors_003.png",
+                "misc_assets/spaceMeteors_004.png", "misc_assets/meteorGrey_big1.png", "misc_assets/meteorGrey_big2.png",
+                "misc_assets/meteorGrey_big3.png", "misc_assets/meteorGrey_big4.png"};
+        break;
     case GAME_CAVEFLYER:  // caveflyer.cpp:36-54
         g.bg_group = "space_backgrounds";
         T[1] = {"misc_assets/ufoGreen2.png"};

@@ -22,6 +22,7 @@
 #include "pg_asset_tables.h"
 #include "pg_kernels.cuh"
 #include "games/bigfish.cuh"
+#include "games/bossfight.cuh"
 #include "games/caveflyer.cuh"
 #include "games/chaser.cuh"
 #include "games/climber.cuh"
@@ -249,6 +250,7 @@ GameVTable make_vtable(int id) {
 const GameVTable *find_game(const std::string &name) {
     static const GameVTable table[] = {
         make_vtable<BigFish>(GAME_BIGFISH),
+        make_vtable<BossfightGame>(GAME_BOSSFIGHT),
         make_vtable<CaveFlyerGame>(GAME_CAVEFLYER),
         make_vtable<ChaserGame>(GAME_CHASER),
         make_vtable<Climber>(GAME_CLIMBER),
