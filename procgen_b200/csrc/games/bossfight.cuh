@@ -16,11 +16,11 @@ struct BossfightState {
 
 struct BossfightGame : Defaults<BossfightGame>, DrawDefaults<BossfightGame> {
     using E = Engine<BossfightGame>;
-    static constexpr int ENT_CAP = 256;
+    static constexpr int ENT_CAP = 384;
     static constexpr int GRID_CAP = 20 * 20;
     static constexpr int SCRATCH_WORDS = 0;
-    static constexpr int MAX_VISIBLE_ENTS = 256;
-    static constexpr int MAX_ROT_BLITS = 192;  // every enemy bullet and its trails spin (vrot = PI/8)
+    static constexpr int MAX_VISIBLE_ENTS = 384;
+    static constexpr int MAX_ROT_BLITS = 352;  // every enemy bullet and its trails spin (vrot = PI/8)
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "bossfight";
 

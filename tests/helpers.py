@@ -34,3 +34,9 @@ def run_lockstep(ref, dut, steps, seed=0, rgb_tol=0):
         ref.act(acts[t])
         dut.act(acts[t])
         assert_same_observation(ref, dut, t, rgb_tol)
+    if hasattr(dut.lib, "pgb200_get_errors"):
+        import ctypes as C
+
+        dut.lib.pgb200_get_errors.restype = C.c_uint32
+        err = dut.lib.pgb200_get_errors(C.c_void_p(dut.h), None)
+        assert err == 0, f"device latched error bits {err:#x} (capacity overflow / unsupported feature)"
