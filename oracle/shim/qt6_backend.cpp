@@ -19,7 +19,7 @@ struct RQBrush { void *d; };
 struct RQPen { void *d; };
 struct RQRectF { double x, y, w, h; };
 struct RQPointF { double x, y; };
-struct RQLineF { double x1, y1, x2, y2; };
+struct RQLine { int x1, y1, x2, y2; };  // QLine: two QPoints of ints
 struct RQColor { int32_t spec; uint16_t a, r, g, b, pad; };
 
 void rq_image_ctor(RQImage *self, unsigned char *data, int w, int h, long long bpl, int format, void (*cleanup)(void *), void *info)
@@ -37,7 +37,7 @@ void rq_painter_save(RQPainter *self) asm("_ZN8QPainter4saveEv");
 void rq_painter_restore(RQPainter *self) asm("_ZN8QPainter7restoreEv");
 void rq_painter_set_render_hint(RQPainter *self, int hint, bool on) asm("_ZN8QPainter13setRenderHintENS_10RenderHintEb");
 void rq_painter_draw_ellipse(RQPainter *self, const RQRectF *r) asm("_ZN8QPainter11drawEllipseERK6QRectF");
-void rq_painter_draw_lines(RQPainter *self, const RQLineF *lines, int n) asm("_ZN8QPainter9drawLinesEPK6QLineFi");
+void rq_painter_draw_lines(RQPainter *self, const RQLine *lines, int n) asm("_ZN8QPainter9drawLinesEPK5QLinei");
 void rq_painter_set_brush(RQPainter *self, const RQBrush *b) asm("_ZN8QPainter8setBrushERK6QBrush");
 void rq_painter_set_pen(RQPainter *self, const RQPen *p) asm("_ZN8QPainter6setPenERK4QPen");
 void rq_painter_set_pen_style(RQPainter *self, int style) asm("_ZN8QPainter6setPenEN2Qt8PenStyleE");
@@ -125,7 +125,7 @@ void QPainter::drawEllipse(const QRectF &r) {
     RQRectF rr{r.x(), r.y(), r.width(), r.height()};
     rq_painter_draw_ellipse(&d->p, &rr);
 }
-void QPainter::drawLine(qreal x1, qreal y1, qreal x2, qreal y2) {
-    RQLineF l{x1, y1, x2, y2};
+void QPainter::drawLine(int x1, int y1, int x2, int y2) {
+    RQLine l{x1, y1, x2, y2};
     rq_painter_draw_lines(&d->p, &l, 1);
 }

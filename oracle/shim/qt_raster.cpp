@@ -28,8 +28,11 @@
 
 // ---------------------------------------------------------------- helpers
 
+// Qt 6's qRound (qnumeric.h): half away from zero. Qt 5 rounded negative ties UP
+// (int(d - double(int(d-1)) + 0.5) + int(d-1)); the two differ only for values exactly on -n.5.
+// The oracle is pinned against Qt 6.6.3, so its form is the one restated.
 static inline int qRound(double d) {
-    return d >= 0.0 ? int(d + 0.5) : int(d - double(int(d - 1)) + 0.5) + int(d - 1);
+    return d >= 0.0 ? int(d + 0.5) : int(d - 0.5);
 }
 
 static inline uint32_t BYTE_MUL(uint32_t x, uint32_t a) {
@@ -863,6 +866,10 @@ static void draw_rotated(QImage *dev, const QImage &img, const QRectF &r, const 
 void QPainter::drawImage(const QRectF &target, const QImage &image) {
     const Xform &m = d->cur.m;
     int io = int(d->cur.opacity * 256);
+    static const bool trace = getenv("QT_SHIM_TRACE") != nullptr;
+    if (trace && d->dev->w == 64)
+        fprintf(stderr, "drawImage %.17g %.17g %.17g %.17g img %dx%d rot %d dx %.17g dy %.17g io %d\n", target.x(), target.y(), target.width(),
+                target.height(), image.width(), image.height(), (int)m.rotated, m.dx, m.dy, io);
     if (!m.rotated) {
         draw_scaled(d->dev, image, QRectF(target.x() + m.dx, target.y() + m.dy, target.width(), target.height()), io);
     } else if (fabs(m.m12) <= 1e-12 && fabs(m.m21) <= 1e-12) {
@@ -875,51 +882,224 @@ void QPainter::drawImage(const QRectF &target, const QImage &image) {
     }
 }
 
-// Non-AA ellipse / line (jumper compass only, jumper.cpp:137-169). Simple centre-sampling
-// restatement; NOT verified against Qt — see DESIGN.md "open parity items".
-void QPainter::drawEllipse(const QRectF &r) {
-    QImage *dev = d->dev;
-    uint32_t *px = dev->pixels();
-    double cx = r.x() + r.width() / 2, cy = r.y() + r.height() / 2;
-    double rx = r.width() / 2, ry = r.height() / 2;
-    if (rx <= 0 || ry <= 0)
+// ---------------------------------------------------------------- ellipse and cosmetic line
+// Used by the jumper compass only (jumper.cpp:137-169). Both are integer algorithms in Qt's raster
+// engine and are restated here; tests/test_oracle.py sweeps them against the real Qt 6 backend.
+
+// solid-colour span, clipped to the device (QSpanData solid blend: src-over with the premultiplied colour)
+static void solid_span(QImage *dev, int x, int len, int y, uint32_t pm, int io) {
+    if (y < 0 || y >= dev->h || len <= 0)
         return;
-    int io = int(d->cur.opacity * 256);
-    const QColor &c = d->cur.brush.on ? d->cur.brush.color : d->cur.pen.color;
-    uint32_t argb = (uint32_t(c.alpha()) << 24) | (uint32_t(c.red()) << 16) | (uint32_t(c.green()) << 8) | uint32_t(c.blue());
-    uint32_t pm = qPremultiply(argb);
-    double pad = d->cur.pen.on ? d->cur.pen.width / 2 : 0;
-    for (int y = std::max(0, int(floor(cy - ry - pad))); y <= std::min(dev->h - 1, int(ceil(cy + ry + pad))); y++)
-        for (int x = std::max(0, int(floor(cx - rx - pad))); x <= std::min(dev->w - 1, int(ceil(cx + rx + pad))); x++) {
-            double u = (x + 0.5 - cx) / (rx + pad), v = (y + 0.5 - cy) / (ry + pad);
-            if (u * u + v * v <= 1.0)
-                blend_px(&px[y * dev->stride + x], pm, io);
-        }
+    int x0 = std::max(x, 0), x1 = std::min(x + len, dev->w);
+    uint32_t *row = dev->pixels() + (size_t)y * dev->stride;
+    for (int xx = x0; xx < x1; xx++) blend_px(&row[xx], pm, io);
 }
 
-void QPainter::drawLine(qreal x1, qreal y1, qreal x2, qreal y2) {
-    QImage *dev = d->dev;
-    uint32_t *px = dev->pixels();
+static uint32_t premul_color(const QColor &c) {
+    uint32_t argb = (uint32_t(c.alpha()) << 24) | (uint32_t(c.red()) << 16) | (uint32_t(c.green()) << 8) | uint32_t(c.blue());
+    return qPremultiply(argb);
+}
+
+struct EllipseCtx {
+    QImage *dev;
+    int rx, ry, rw, rh;  // integer rect
+    bool pen, brush;
+    uint32_t pen_pm, brush_pm;
+    int io;
+};
+
+// drawEllipsePoints (qpaintengine_raster.cpp): the four mirrored outline spans of one octant step
+// plus the two fill spans between them
+static void ellipse_points(const EllipseCtx &e, int x, int y, int length) {
+    if (length == 0)
+        return;
+    const int midx = e.rx + (e.rw + 1) / 2;
+    const int midy = e.ry + (e.rh + 1) / 2;
+    x = x + midx;
+    y = midy - y;
+    int ox[4], ol[4], oy[4];
+    ox[0] = midx + (midx - x) - (length - 1) - (e.rw & 0x1);  // top left
+    ol[0] = std::min(length, x - ox[0]);
+    oy[0] = y;
+    ox[1] = x;  // top right
+    ol[1] = length;
+    oy[1] = y;
+    ox[2] = ox[0];  // bottom left
+    ol[2] = ol[0];
+    oy[2] = midy + (midy - y) - (e.rh & 0x1);
+    ox[3] = x;  // bottom right
+    ol[3] = length;
+    oy[3] = oy[2];
+    if (e.brush && ox[0] + ol[0] < ox[1]) {
+        int fx0 = ox[0] + ol[0] - 1;
+        int fl0 = std::max(0, ox[1] - fx0);
+        int fx1 = ox[2] + ol[2] - 1;
+        int fl1 = std::max(0, ox[3] - fx1);
+        int n = (oy[1] >= oy[3]) ? 1 : 2;
+        solid_span(e.dev, fx0, fl0, oy[1], e.brush_pm, e.io);
+        if (n == 2)
+            solid_span(e.dev, fx1, fl1, oy[3], e.brush_pm, e.io);
+    }
+    if (e.pen) {
+        int n = (oy[1] >= oy[2]) ? 2 : 4;
+        for (int i = 0; i < n; i++) solid_span(e.dev, ox[i], ol[i], oy[i], e.pen_pm, e.io);
+    }
+}
+
+// drawEllipse_midpoint_i (qpaintengine_raster.cpp)
+static void ellipse_midpoint(const EllipseCtx &e) {
+    const double a = double(e.rw) / 2;
+    const double b = double(e.rh) / 2;
+    double d = b * b - (a * a * b) + 0.25 * a * a;
+    int x = 0;
+    int y = (e.rh + 1) / 2;
+    int startx = x;
+    // region 1
+    while (a * a * (2 * y - 1) > 2 * b * b * (x + 1)) {
+        if (d < 0) {
+            d += b * b * (2 * x + 3);
+            ++x;
+        } else {
+            d += b * b * (2 * x + 3) + a * a * (-2 * y + 2);
+            ellipse_points(e, startx, y, x - startx + 1);
+            startx = ++x;
+            --y;
+        }
+    }
+    ellipse_points(e, startx, y, x - startx + 1);
+    // region 2
+    d = b * b * (x + 0.5) * (x + 0.5) + a * a * ((y - 1) * (y - 1) - b * b);
+    const int miny = e.rh & 0x1;
+    while (y > miny) {
+        if (d < 0) {
+            d += b * b * (2 * x + 2) + a * a * (-2 * y + 3);
+            ++x;
+        } else {
+            d += a * a * (-2 * y + 3);
+        }
+        --y;
+        ellipse_points(e, x, y, 1);
+    }
+}
+
+// QRasterPaintEngine::drawEllipse, non-antialiased, unrotated, pen <= 1 px or none.
+//  * integer-aligned rect (jumper hard mode's compass disc at (55,1,8,8); every QRect ellipse):
+//    Qt 6.6.3 runs the midpoint algorithm above — swept against the real library, all rects.
+//  * any other rect goes through Qt's generic path code (Bezier flattening + scan conversion + a
+//    cosmetic stroke of the outline). The only such call in scope is jumper easy mode's disc,
+//    whose rect is a constant of the 64x64 contract (visibility 12, compass_dim 3): its pixel
+//    rows were captured once from Qt 6.6.3 (tools/qt6_compass_mask.py) and are replayed here.
+//    Anything else is reported, never approximated.
+struct EllipseRowSpan { int y, x1, x2; };
+static const double kCompassEasyRect[4] = {46.66666793823242, 1.3333333730697632, 16.0, 16.0};
+static const EllipseRowSpan kCompassEasyRows[] = {{1, 52, 58},  {2, 50, 59},  {3, 49, 60},  {4, 48, 61},  {5, 48, 62},  {6, 47, 63},
+                                                  {7, 47, 63},  {8, 46, 63},  {9, 46, 63},  {10, 46, 63}, {11, 47, 63}, {12, 47, 63},
+                                                  {13, 47, 62}, {14, 48, 61}, {15, 49, 60}, {16, 51, 59}, {17, 53, 57}};
+
+void QPainter::drawEllipse(const QRectF &rr) {
+    const Xform &m = d->cur.m;
+    const double x = rr.x() * m.m11 + m.dx, y = rr.y() * m.m22 + m.dy, w = rr.width() * m.m11, h = rr.height() * m.m22;
+    const int io = int(d->cur.opacity * 256);
+    const bool integral = x == std::floor(x) && y == std::floor(y) && w == std::floor(w) && h == std::floor(h);
+    if (!integral) {
+        const bool same_opaque = d->cur.pen.on && d->cur.brush.on && d->cur.pen.color.alpha() == 255 &&
+                                 premul_color(d->cur.pen.color) == premul_color(d->cur.brush.color);
+        if (x == kCompassEasyRect[0] && y == kCompassEasyRect[1] && w == kCompassEasyRect[2] && h == kCompassEasyRect[3] && same_opaque &&
+            d->dev->w == 64 && d->dev->h == 64) {
+            for (const EllipseRowSpan &r : kCompassEasyRows) solid_span(d->dev, r.x1, r.x2 - r.x1, r.y, premul_color(d->cur.pen.color), io);
+            return;
+        }
+        fprintf(stderr, "qt shim: drawEllipse on a non-integer rect (%.17g %.17g %.17g %.17g) is outside the restated subset\n", x, y, w, h);
+        abort();
+    }
+    EllipseCtx e;
+    e.dev = d->dev;
+    e.rx = int(x);
+    e.ry = int(y);
+    e.rw = int(x + w) - int(x);
+    e.rh = int(y + h) - int(y);
+    if (e.rw <= 0 || e.rh <= 0)
+        return;
+    e.pen = d->cur.pen.on;
+    e.brush = d->cur.brush.on;
+    e.pen_pm = premul_color(d->cur.pen.color);
+    e.brush_pm = premul_color(d->cur.brush.color);
+    e.io = io;
+    ellipse_midpoint(e);
+}
+
+// QCosmeticStroker::drawLine for one isolated line with square caps (the default QPen cap), integer
+// end points, non-antialiased, no dashes. 26.6 end points, 16.16 minor-axis stepping.
+static inline int fdot16_div(int x, int y) {
+    if (std::abs(x) > 0x7fff)
+        return int((long long)x * (1 << 16) / y);
+    return x * (1 << 16) / y;
+}
+void QPainter::drawLine(int ix1, int iy1, int ix2, int iy2) {
     if (!d->cur.pen.on)
         return;
-    const QColor &c = d->cur.pen.color;
-    uint32_t argb = (uint32_t(c.alpha()) << 24) | (uint32_t(c.red()) << 16) | (uint32_t(c.green()) << 8) | uint32_t(c.blue());
-    uint32_t pm = qPremultiply(argb);
-    int io = int(d->cur.opacity * 256);
-    double hw = std::max(d->cur.pen.width, 1.0) / 2;
-    double dx = x2 - x1, dy = y2 - y1;
-    double len2 = dx * dx + dy * dy;
-    int bx0 = std::max(0, int(floor(std::min(x1, x2) - hw))), bx1 = std::min(dev->w - 1, int(ceil(std::max(x1, x2) + hw)));
-    int by0 = std::max(0, int(floor(std::min(y1, y2) - hw))), by1 = std::min(dev->h - 1, int(ceil(std::max(y1, y2) + hw)));
-    for (int y = by0; y <= by1; y++)
-        for (int x = bx0; x <= bx1; x++) {
-            double pxc = x + 0.5 - x1, pyc = y + 0.5 - y1;
-            double t = len2 > 0 ? (pxc * dx + pyc * dy) / len2 : 0;
-            t = std::min(1.0, std::max(0.0, t));
-            double ex = pxc - t * dx, ey = pyc - t * dy;
-            if (ex * ex + ey * ey <= hw * hw)
-                blend_px(&px[y * dev->stride + x], pm, io);
+    QImage *dev = d->dev;
+    const Xform &m = d->cur.m;
+    const uint32_t pm = premul_color(d->cur.pen.color);
+    const int io = int(d->cur.opacity * 256);
+    const double rx1 = ix1 * m.m11 + m.dx, ry1 = iy1 * m.m22 + m.dy, rx2 = ix2 * m.m11 + m.dx, ry2 = iy2 * m.m22 + m.dy;
+    if (rx1 == rx2 && ry1 == ry2) {  // drawPoints: one pixel
+        solid_span(dev, int(std::floor(rx1)), 1, int(std::floor(ry1)), pm, io);
+        return;
+    }
+    enum { CapBegin = 1, CapEnd = 2 };
+    int caps = CapBegin | CapEnd;
+    int x1 = int(rx1 * 64.), x2 = int(rx2 * 64.), y1 = int(ry1 * 64.), y2 = int(ry2 * 64.);
+    const int dx = std::abs(x2 - x1), dy = std::abs(y2 - y1);
+    if (dx < dy) {
+        if (y1 > y2) {
+            std::swap(y1, y2);
+            std::swap(x1, x2);
         }
+        const int xinc = fdot16_div(x2 - x1, y2 - y1);
+        int x = x1 * (1 << 10);
+        if (caps & CapBegin) {
+            y1 -= 32;
+            x -= xinc >> 1;
+        }
+        if (caps & CapEnd)
+            y2 += 32;
+        int y = (y1 + 32) >> 6;
+        const int ys = (y2 + 32) >> 6;
+        const int round = (xinc > 0) ? 32 : 0;
+        if (y != ys) {
+            x += ((y * (1 << 6)) + round - y1) * xinc >> 6;
+            do {
+                solid_span(dev, x >> 16, 1, y, pm, io);
+                x += xinc;
+            } while (++y < ys);
+        }
+    } else {
+        if (!dx)
+            return;
+        if (x1 > x2) {
+            std::swap(x1, x2);
+            std::swap(y1, y2);
+        }
+        const int yinc = fdot16_div(y2 - y1, x2 - x1);
+        int y = y1 * (1 << 10);
+        if (caps & CapBegin) {
+            x1 -= 32;
+            y -= yinc >> 1;
+        }
+        if (caps & CapEnd)
+            x2 += 32;
+        int x = (x1 + 32) >> 6;
+        const int xs = (x2 + 32) >> 6;
+        const int round = (yinc > 0) ? 32 : 0;
+        if (x != xs) {
+            y += ((x * (1 << 6)) + round - x1) * yinc >> 6;
+            do {
+                solid_span(dev, x, 1, y >> 16, pm, io);
+                y += yinc;
+            } while (++x < xs);
+        }
+    }
 }
 
 #endif  // QT_SHIM_QT6_BACKEND

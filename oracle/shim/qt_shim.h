@@ -173,7 +173,7 @@ class QPainter {
     void setPen(Qt::PenStyle s) { setPen(QPen(s)); }
     void drawEllipse(const QRectF &r);
     void drawEllipse(const QRect &r) { drawEllipse(QRectF(r)); }
-    void drawLine(qreal x1, qreal y1, qreal x2, qreal y2);
+    void drawLine(int x1, int y1, int x2, int y2);  // the only four-number overload Qt has: callers truncate
     void setCompositionMode(CompositionMode m);
 
     struct State;

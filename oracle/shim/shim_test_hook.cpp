@@ -33,3 +33,26 @@ extern "C" __attribute__((visibility("default"))) void shim_test_fill_rect(uint3
     QPainter p(&dev);
     p.fillRect(QRectF(x, y, rw, rh), QColor(r, g, b));
 }
+
+// drawEllipse / drawLine exactly as jumper.cpp:137-169 issues them: set_pen_brush_color (pen and
+// brush of one colour, integer pen width) or brush-only with Qt::NoPen.
+extern "C" __attribute__((visibility("default"))) void shim_test_draw_ellipse(uint32_t *dst, int w, int h, double x, double y, double rw,
+                                                                               double rh, int r, int g, int b, int a, int pen_width) {
+    QImage dev((uchar *)dst, w, h, w * 4, QImage::Format_RGB32);
+    QPainter p(&dev);
+    p.setBrush(QBrush(QColor(r, g, b, a)));
+    if (pen_width < 0)
+        p.setPen(Qt::NoPen);
+    else
+        p.setPen(QPen(QColor(r, g, b, a), pen_width));
+    p.drawEllipse(QRectF(x, y, rw, rh));
+}
+
+extern "C" __attribute__((visibility("default"))) void shim_test_draw_line(uint32_t *dst, int w, int h, int x1, int y1, int x2, int y2,
+                                                                            int r, int g, int b, int pen_width) {
+    QImage dev((uchar *)dst, w, h, w * 4, QImage::Format_RGB32);
+    QPainter p(&dev);
+    p.setBrush(QBrush(QColor(r, g, b)));
+    p.setPen(QPen(QColor(r, g, b), pen_width));
+    p.drawLine(x1, y1, x2, y2);
+}

@@ -164,6 +164,47 @@ inline GameAssetNames game_asset_names(int game_id) {
         T[9] = {"misc_assets/dirt.png"};
         T[10] = {"misc_assets/tile_bricksGrey.png"};
         break;
+    case GAME_DODGEBALL:  // dodgeball.cpp:46-88
+        g.bg_group = "topdown_backgrounds";
+        T[0] = {"misc_assets/character12.png"};
+        T[3] = {"misc_assets/ball_soccer1.png"};
+        for (int i = 1; i <= 11; i++) T[4].push_back("misc_assets/character" + std::to_string(i) + ".png");
+        T[5] = {"misc_assets/blockRed.png"};
+        T[6] = {"misc_assets/ball_soccer2.png"};
+        T[7] = {"misc_assets/blockGreen.png"};
+        T[1] = {"misc_assets/tileStone_slope2.png"};
+        T[10] = {"misc_assets/tileStone_slope2.png"};
+        for (int i = 1; i <= 9; i++) T[8].push_back("misc_assets/spaceEffect" + std::to_string(i) + ".png");
+        break;
+    case GAME_STARPILOT:  // starpilot.cpp:55-108
+        g.bg_group = "space_backgrounds";
+        T[0] = {"misc_assets/playerShip2_blue.png"};
+        T[1] = {"misc_assets/towerDefense_tile295.png"};
+        T[2] = {"misc_assets/towerDefense_tile296.png"};
+        T[3] = {"misc_assets/towerDefense_tile297.png"};
+        for (int i = 1; i <= 7; i++) {
+            T[4].push_back("misc_assets/spaceShips_00" + std::to_string(i) + ".png");
+            T[8].push_back("misc_assets/spaceShips_00" + std::to_string(i) + ".png");
+        }
+        for (int i = 1; i <= 4; i++) T[5].push_back("misc_assets/spaceMeteors_00" + std::to_string(i) + ".png");
+        for (int i = 1; i <= 4; i++) T[5].push_back("misc_assets/meteorGrey_big" + std::to_string(i) + ".png");
+        for (int i = 1; i <= 9; i++) T[6].push_back("misc_assets/spaceEffect" + std::to_string(i) + ".png");
+        T[7] = {"misc_assets/spaceStation_018.png", "misc_assets/spaceStation_019.png"};
+        for (int i = 1; i <= 4; i++) T[9].push_back("misc_assets/spaceRockets_00" + std::to_string(i) + ".png");
+        break;
+    case GAME_JUMPER:  // jumper.cpp:50-78
+        g.bg_group = "platform_backgrounds";
+        T[0] = {"misc_assets/bunny2_ready.png"};
+        T[2] = {"misc_assets/spikeMan_stand.png"};
+        T[1] = {"misc_assets/carrot.png"};
+        T[9] = {"misc_assets/bunny2_jump.png"};
+        T[12] = {"misc_assets/bunny2_walk1.png"};
+        T[13] = {"misc_assets/bunny2_walk2.png"};
+        T[10] = {"misc_assets/bunny2_walk1.png"};
+        T[11] = {"misc_assets/bunny2_walk2.png"};
+        T[7] = {"platformer/tileBlue_05.png", "platformer/tileGreen_05.png", "platformer/tileYellow_06.png", "platformer/tileBrown_06.png"};
+        T[6] = {"platformer/tileBlue_08.png", "platformer/tileGreen_08.png", "platformer/tileYellow_09.png", "platformer/tileBrown_09.png"};
+        break;
     default:
         throw std::runtime_error("procgen_b200: game id " + std::to_string(game_id) + " has no asset table yet");
     }

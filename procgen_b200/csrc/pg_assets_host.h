@@ -211,10 +211,12 @@ struct AtlasBuilder {
         for (auto &kv : names.by_type) {
             int type = kv.first;
             const auto &list = kv.second;
-            if (type < 0 || type >= MAX_ASSETS || list.size() > (size_t)MAX_IMAGE_THEMES)
+            if (type < 0 || type >= MAX_ASSETS)
                 throw std::runtime_error("bad asset table");
+            // asset_num_themes is the full list length even when it exceeds the MAX_IMAGE_THEMES
+            // slots the reference can address (dodgeball lists 11 enemies and draws from the first 7)
             ga.num_themes[type] = (int32_t)list.size();
-            for (size_t theme = 0; theme < list.size(); theme++) {
+            for (size_t theme = 0; theme < list.size() && theme < (size_t)MAX_IMAGE_THEMES; theme++) {
                 SpriteDesc d = add(list[theme], true);
                 int idx = type + (int)theme * MAX_ASSETS;
                 ga.sprites[idx] = d;

@@ -92,6 +92,126 @@ PG_HD double pg_dfloor(double x) { return floor(x); }
 PG_HD double pg_dceil(double x) { return ceil(x); }
 PG_HD double pg_dfabs(double x) { return fabs(x); }
 
+// ---- atan2f exactly as the oracle's C library computes it.
+// Entity::face_direction (entity.cpp:84-88) calls atan2 on floats with <math.h> in scope, which
+// binds to atan2f (checked in the oracle's object code). glibc 2.39's atan2f/atanf (the fdlibm
+// single-precision kernels, sysdeps/ieee754/flt-32/e_atan2f.c + s_atanf.c) are NOT correctly
+// rounded — they differ from round(atan2(double)) on ~16% of inputs — so the float operation
+// sequence is restated here: same reduction intervals, same coefficient bits, no FMA (device code
+// is built with -fmad=false). tests/native/atan2f_check.cpp diffs it against the host libm.
+PG_HD int32_t pg_float_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    union { float f; int32_t i; } u;
+    u.f = f;
+    return u.i;
+#endif
+}
+PG_HD float pg_bits_float(int32_t i) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    union { float f; int32_t i; } u;
+    u.i = i;
+    return u.f;
+#endif
+}
+PG_HD float pg_atanf(float x) {
+    const float hi0 = pg_bits_float(0x3eed6338), hi1 = pg_bits_float(0x3f490fda), hi2 = pg_bits_float(0x3f7b985e), hi3 = pg_bits_float(0x3fc90fda);
+    const float lo0 = pg_bits_float(0x31ac3769), lo1 = pg_bits_float(0x33222168), lo2 = pg_bits_float(0x33140fb4), lo3 = pg_bits_float(0x33a22168);
+    const float aT0 = pg_bits_float(0x3eaaaaab), aT1 = pg_bits_float((int32_t)0xbe4ccccd), aT2 = pg_bits_float(0x3e124925),
+                aT3 = pg_bits_float((int32_t)0xbde38e38), aT4 = pg_bits_float(0x3dba2e6e), aT5 = pg_bits_float((int32_t)0xbd9d8795),
+                aT6 = pg_bits_float(0x3d886b35), aT7 = pg_bits_float((int32_t)0xbd6ef16b), aT8 = pg_bits_float(0x3d4bda59),
+                aT9 = pg_bits_float((int32_t)0xbd15a221), aT10 = pg_bits_float(0x3c8569d7);
+    const int32_t hx = pg_float_bits(x);
+    const int32_t ix = hx & 0x7fffffff;
+    float hi = 0, lo = 0;
+    int id;
+    if (ix >= 0x4c000000) {  // |x| >= 2^25
+        if (ix > 0x7f800000)
+            return x + x;
+        return hx > 0 ? hi3 + lo3 : -hi3 - lo3;
+    }
+    if (ix < 0x3ee00000) {  // |x| < 0.4375
+        if (ix < 0x31000000)
+            return x;
+        id = -1;
+    } else {
+        x = pg_bits_float(ix);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) {
+                id = 0; hi = hi0; lo = lo0;
+                x = (2.0f * x - 1.0f) / (2.0f + x);
+            } else {
+                id = 1; hi = hi1; lo = lo1;
+                x = (x - 1.0f) / (x + 1.0f);
+            }
+        } else {
+            if (ix < 0x401c0000) {
+                id = 2; hi = hi2; lo = lo2;
+                x = (x - 1.5f) / (1.0f + 1.5f * x);
+            } else {
+                id = 3; hi = hi3; lo = lo3;
+                x = -1.0f / x;
+            }
+        }
+    }
+    const float z = x * x;
+    const float w = z * z;
+    const float s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    const float s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    if (id < 0)
+        return x - x * (s1 + s2);
+    const float r = hi - ((x * (s1 + s2) - lo) - x);
+    return hx < 0 ? -r : r;
+}
+PG_HD float pg_atan2f(float y, float x) {
+    const float tiny = 1.0e-30f;
+    const float pi_o_4 = pg_bits_float(0x3f490fdb), pi_o_2 = pg_bits_float(0x3fc90fdb), pi = pg_bits_float(0x40490fdb),
+                pi_lo = pg_bits_float((int32_t)0xb3bbbd2e);
+    const int32_t hx = pg_float_bits(x), hy = pg_float_bits(y);
+    const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000)
+        return x + y;
+    if (hx == 0x3f800000)
+        return pg_atanf(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);  // 2*sign(x) + sign(y)
+    if (iy == 0) {
+        if (m < 2)
+            return y;
+        return m == 2 ? pi + tiny : -pi - tiny;
+    }
+    if (ix == 0)
+        return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    if (ix == 0x7f800000) {
+        if (iy == 0x7f800000) {
+            if (m == 0) return pi_o_4 + tiny;
+            if (m == 1) return -pi_o_4 - tiny;
+            if (m == 2) return 3.0f * pi_o_4 + tiny;
+            return -3.0f * pi_o_4 - tiny;
+        }
+        if (m == 0) return 0.0f;
+        if (m == 1) return -0.0f;
+        if (m == 2) return pi + tiny;
+        return -pi - tiny;
+    }
+    if (iy == 0x7f800000)
+        return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60)
+        z = pi_o_2 + 0.5f * pi_lo;
+    else if (hx < 0 && k < -60)
+        z = 0.0f;
+    else
+        z = pg_atanf(pg_bits_float(pg_float_bits(y / x) & 0x7fffffff));
+    if (m == 0) return z;
+    if (m == 1) return pg_bits_float(pg_float_bits(z) ^ (int32_t)0x80000000);
+    if (m == 2) return pi - (z - pi_lo);
+    return (z - pi_lo) - pi;
+}
+
 // cpp-utils.h:43-45 — returns double on purpose
 PG_HD double pg_sign(double x) { return x > 0 ? +1 : (x == 0 ? 0 : -1); }
 
@@ -104,9 +224,10 @@ PG_HD float pg_clip_abs(float x, float y) {
     return x;
 }
 
-// Qt's qRound(double) (qglobal.h) — round half up, used by every raster rule
+// Qt 6's qRound(double) (qnumeric.h) — half away from zero, used by every raster rule. (Qt 5
+// rounded exact negative ties up; the oracle is pinned against Qt 6.6.3.)
 PG_HD int pg_qround(double d) {
-    return d >= 0.0 ? int(d + 0.5) : int(d - double(int(d - 1)) + 0.5) + int(d - 1);
+    return d >= 0.0 ? int(d + 0.5) : int(d - 0.5);
 }
 
 // Qt's BYTE_MUL on a packed 0xAARRGGBB word (qdrawhelper_p.h)

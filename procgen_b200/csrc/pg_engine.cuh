@@ -84,12 +84,12 @@ PG_HD void entity_step(Entity &e) {
     e.alpha = e.alpha_decay * e.alpha;
 }
 
-// entity.cpp:84-88. entity.cpp includes <math.h>, so this atan2 is the FLOAT overload (atan2f in the
-// oracle's object code) and the whole expression is float arithmetic. atan2f is taken as the
-// correctly rounded value: the double result rounded to float (CUDA's own atan2f is only 3-ulp).
+// entity.cpp:84-88. entity.cpp includes <math.h>, so this atan2 is the FLOAT function (atan2f in the
+// oracle's object code) and the whole expression is float arithmetic; pg_atan2f reproduces the C
+// library's (not correctly rounded) result bit for bit.
 PG_HD void entity_face_direction(Entity &e, float dx, float dy, float rotation_offset = 0) {
     if (dx != 0 || dy != 0)
-        e.rotation = -1 * (float)atan2((double)dy, (double)dx) + rotation_offset;
+        e.rotation = -1 * pg_atan2f(dy, dx) + rotation_offset;
 }
 
 PG_HD Entity &agent_of(Ctx &c) { return c.ents[c.h->agent_idx]; }

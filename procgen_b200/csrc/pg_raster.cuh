@@ -25,7 +25,7 @@
 
 namespace pg {
 
-enum BlitKind : uint8_t { BLIT_NONE = 0, BLIT_IMAGE = 1, BLIT_SOLID = 2, BLIT_ROTATED = 3 };
+enum BlitKind : uint8_t { BLIT_NONE = 0, BLIT_IMAGE = 1, BLIT_SOLID = 2, BLIT_ROTATED = 3, BLIT_SPANS = 4 };
 
 struct Blit {
     uint8_t x1, y1, w, h;    // device pixels [x1,x1+w) x [y1,y1+h) after clip + Qt's edge guards;
@@ -586,6 +586,12 @@ PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uin
         return dst;
     if (b.kind == BLIT_SOLID)
         return b.src;
+    if (b.kind == BLIT_SPANS) {  // one solid-colour span per row (ellipse / cosmetic line), src-over
+        const RotBlit &rb = rots[b.ix];
+        if (px < (int)rb.x1[py] || px >= (int)rb.x2[py])
+            return dst;
+        return blend_px(dst, b.src, 256);
+    }
     if (b.kind == BLIT_ROTATED) {
         const RotBlit &rb = rots[b.ix];
         const int xs = rb.x1[py];
@@ -618,6 +624,198 @@ PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uin
         sx = b.sw - 1 - sx;
     uint32_t texel = atlas[b.src + sy * b.sw + sx];
     return blend_px(dst, texel, b.opacity);
+}
+
+// ---- rules E / L: QPainter::drawEllipse and drawLine as the raster engine runs them for the
+// jumper compass (jumper.cpp:137-169); oracle/shim/qt_raster.cpp has the provenance and the sweep
+// against Qt 6.6.3. Both produce one span per pixel row, kept in a RotBlit slot taken from the END
+// of the frame's rot array (entity rotations allocate from the front).
+template <class Frame>
+PG_HD RotBlit *span_blit_begin(Frame &f, Blit &b, int k, uint32_t argb_premultiplied) {
+    blit_clear(b);
+    const int slot = Frame::kMaxRot - 1 - k;
+    if (slot < 0)
+        return nullptr;
+    RotBlit &rb = f.rot[slot];
+    for (int y = 0; y < RES_H; y++) rb.x1[y] = rb.x2[y] = 0;
+    b.ix = slot;
+    b.src = argb_premultiplied;
+    b.opacity = 256;
+    return &rb;
+}
+PG_HD void span_blit_finish(Blit &b, const RotBlit &rb) {
+    int y0 = RES_H, y1 = -1, x0 = RES_W, x1 = 0;
+    for (int y = 0; y < RES_H; y++) {
+        if (rb.x2[y] > rb.x1[y]) {
+            if (y < y0) y0 = y;
+            y1 = y;
+            if (rb.x1[y] < x0) x0 = rb.x1[y];
+            if (rb.x2[y] > x1) x1 = rb.x2[y];
+        }
+    }
+    if (y1 < y0)
+        return;
+    b.x1 = (uint8_t)x0;
+    b.y1 = (uint8_t)y0;
+    b.w = (uint8_t)(x1 - x0);
+    b.h = (uint8_t)(y1 - y0 + 1);
+    b.kind = BLIT_SPANS;
+}
+
+// drawEllipsePoints (qpaintengine_raster.cpp): mirrored outline spans of one step + the fill between
+PG_HD void ellipse_points(RotBlit &rb, int rx, int ry, int rw, int rh, bool pen, bool brush, int x, int y, int length) {
+    if (length == 0)
+        return;
+    const int midx = rx + (rw + 1) / 2;
+    const int midy = ry + (rh + 1) / 2;
+    x = x + midx;
+    y = midy - y;
+    const int ox0 = midx + (midx - x) - (length - 1) - (rw & 0x1);
+    const int ol0 = length < x - ox0 ? length : x - ox0;
+    const int oy_top = y;
+    const int oy_bot = midy + (midy - y) - (rh & 0x1);
+    if (brush && ox0 + ol0 < x) {
+        const int fx = ox0 + ol0 - 1;
+        const int fl = x - fx > 0 ? x - fx : 0;
+        rot_span(rb, fx, fl, oy_top);
+        if (!(oy_top >= oy_bot))
+            rot_span(rb, fx, fl, oy_bot);
+    }
+    if (pen) {
+        rot_span(rb, ox0, ol0, oy_top);
+        rot_span(rb, x, length, oy_top);
+        if (!(oy_top >= oy_bot)) {
+            rot_span(rb, ox0, ol0, oy_bot);
+            rot_span(rb, x, length, oy_bot);
+        }
+    }
+}
+
+// QRasterPaintEngine::drawEllipse on a device rect (pen at most one pixel wide, same colour as the
+// brush, or no pen). Integer-aligned rects run drawEllipse_midpoint_i; the one non-aligned rect in
+// scope — jumper easy mode's compass disc, a constant of the 64x64 contract — replays the rows
+// captured from Qt 6.6.3 (tools/qt6_compass_mask.py). Returns false for anything else.
+template <class Frame>
+PG_HD bool make_ellipse_blit(Frame &f, Blit &b, int k, double x, double y, double w, double h, uint32_t argb_premultiplied, bool pen) {
+    RotBlit *rbp = span_blit_begin(f, b, k, argb_premultiplied);
+    if (!rbp)
+        return false;
+    RotBlit &rb = *rbp;
+    const bool integral = x == pg_dfloor(x) && y == pg_dfloor(y) && w == pg_dfloor(w) && h == pg_dfloor(h);
+    if (!integral) {
+        if (!(x == 46.66666793823242 && y == 1.3333333730697632 && w == 16.0 && h == 16.0 && pen && (argb_premultiplied >> 24) == 255u))
+            return false;
+        const uint8_t rows[17][2] = {{52, 58}, {50, 59}, {49, 60}, {48, 61}, {48, 62}, {47, 63}, {47, 63}, {46, 63}, {46, 63},
+                                     {46, 63}, {47, 63}, {47, 63}, {47, 62}, {48, 61}, {49, 60}, {51, 59}, {53, 57}};
+        for (int i = 0; i < 17; i++) rot_span(rb, rows[i][0], rows[i][1] - rows[i][0], 1 + i);
+        span_blit_finish(b, rb);
+        return true;
+    }
+    const int rx = (int)x, ry = (int)y;
+    const int rw = (int)(x + w) - (int)x, rh = (int)(y + h) - (int)y;
+    if (rw <= 0 || rh <= 0)
+        return true;
+    const double a = (double)rw / 2;
+    const double bb = (double)rh / 2;
+    double d = bb * bb - (a * a * bb) + 0.25 * a * a;
+    int ex = 0;
+    int ey = (rh + 1) / 2;
+    int startx = ex;
+    while (a * a * (2 * ey - 1) > 2 * bb * bb * (ex + 1)) {  // region 1
+        if (d < 0) {
+            d += bb * bb * (2 * ex + 3);
+            ++ex;
+        } else {
+            d += bb * bb * (2 * ex + 3) + a * a * (-2 * ey + 2);
+            ellipse_points(rb, rx, ry, rw, rh, pen, true, startx, ey, ex - startx + 1);
+            startx = ++ex;
+            --ey;
+        }
+    }
+    ellipse_points(rb, rx, ry, rw, rh, pen, true, startx, ey, ex - startx + 1);
+    d = bb * bb * (ex + 0.5) * (ex + 0.5) + a * a * ((ey - 1) * (ey - 1) - bb * bb);  // region 2
+    const int miny = rh & 0x1;
+    while (ey > miny) {
+        if (d < 0) {
+            d += bb * bb * (2 * ex + 2) + a * a * (-2 * ey + 3);
+            ++ex;
+        } else {
+            d += a * a * (-2 * ey + 3);
+        }
+        --ey;
+        ellipse_points(rb, rx, ry, rw, rh, pen, true, ex, ey, 1);
+    }
+    span_blit_finish(b, rb);
+    return true;
+}
+
+// QCosmeticStroker::drawLine for one isolated line: integer end points (QPainter::drawLine(int...)),
+// square caps, not clipped by the device edge (the caller guarantees it: the compass needle).
+PG_HD int pg_fdot16_div(int x, int y) {
+    int ax = x < 0 ? -x : x;
+    if (ax > 0x7fff)
+        return (int)((long long)x * (1 << 16) / y);
+    return x * (1 << 16) / y;
+}
+template <class Frame>
+PG_HD bool make_line_blit(Frame &f, Blit &b, int k, int ix1, int iy1, int ix2, int iy2, uint32_t argb_premultiplied) {
+    RotBlit *rbp = span_blit_begin(f, b, k, argb_premultiplied);
+    if (!rbp)
+        return false;
+    RotBlit &rb = *rbp;
+    // clipLine's guard band: outside it Qt moves the end points and the stepping changes
+    if (ix1 < 0 || ix1 >= RES_W || ix2 < 0 || ix2 >= RES_W || iy1 < 0 || iy1 >= RES_H || iy2 < 0 || iy2 >= RES_H)
+        return false;
+    if (ix1 == ix2 && iy1 == iy2) {
+        rot_span(rb, ix1, 1, iy1);
+        span_blit_finish(b, rb);
+        return true;
+    }
+    int x1 = ix1 * 64, x2 = ix2 * 64, y1 = iy1 * 64, y2 = iy2 * 64;
+    const int dx = x2 > x1 ? x2 - x1 : x1 - x2, dy = y2 > y1 ? y2 - y1 : y1 - y2;
+    if (dx < dy) {
+        if (y1 > y2) {
+            int t = y1; y1 = y2; y2 = t;
+            t = x1; x1 = x2; x2 = t;
+        }
+        const int xinc = pg_fdot16_div(x2 - x1, y2 - y1);
+        int x = x1 * (1 << 10);
+        y1 -= 32;  // CapBegin
+        x -= xinc >> 1;
+        y2 += 32;  // CapEnd
+        int y = (y1 + 32) >> 6;
+        const int ys = (y2 + 32) >> 6;
+        const int round = (xinc > 0) ? 32 : 0;
+        if (y != ys) {
+            x += ((y * (1 << 6)) + round - y1) * xinc >> 6;
+            do {
+                rot_span(rb, x >> 16, 1, y);
+                x += xinc;
+            } while (++y < ys);
+        }
+    } else {
+        if (x1 > x2) {
+            int t = x1; x1 = x2; x2 = t;
+            t = y1; y1 = y2; y2 = t;
+        }
+        const int yinc = pg_fdot16_div(y2 - y1, x2 - x1);
+        int y = y1 * (1 << 10);
+        x1 -= 32;
+        y -= yinc >> 1;
+        x2 += 32;
+        int x = (x1 + 32) >> 6;
+        const int xs = (x2 + 32) >> 6;
+        const int round = (yinc > 0) ? 32 : 0;
+        if (x != xs) {
+            y += ((x * (1 << 6)) + round - x1) * yinc >> 6;
+            do {
+                rot_span(rb, x, 1, y >> 16);
+                y += yinc;
+            } while (++x < xs);
+        }
+    }
+    span_blit_finish(b, rb);
+    return true;
 }
 
 template <class G, class Frame>

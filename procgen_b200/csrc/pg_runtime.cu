@@ -23,17 +23,20 @@
 #include "pg_kernels.cuh"
 #include "games/bigfish.cuh"
 #include "games/bossfight.cuh"
+#include "games/dodgeball.cuh"
 #include "games/caveflyer.cuh"
 #include "games/chaser.cuh"
 #include "games/climber.cuh"
 #include "games/coinrun.cuh"
 #include "games/fruitbot.cuh"
 #include "games/heist.cuh"
+#include "games/jumper.cuh"
 #include "games/leaper.cuh"
 #include "games/maze.cuh"
 #include "games/miner.cuh"
 #include "games/ninja.cuh"
 #include "games/plunder.cuh"
+#include "games/starpilot.cuh"
 
 #ifndef PG_HOSTSIM
 #include <cuda_runtime.h>
@@ -251,17 +254,20 @@ const GameVTable *find_game(const std::string &name) {
     static const GameVTable table[] = {
         make_vtable<BigFish>(GAME_BIGFISH),
         make_vtable<BossfightGame>(GAME_BOSSFIGHT),
+        make_vtable<DodgeballGame>(GAME_DODGEBALL),
         make_vtable<CaveFlyerGame>(GAME_CAVEFLYER),
         make_vtable<ChaserGame>(GAME_CHASER),
         make_vtable<Climber>(GAME_CLIMBER),
         make_vtable<CoinRun>(GAME_COINRUN),
         make_vtable<FruitBotGame>(GAME_FRUITBOT),
         make_vtable<HeistGame>(GAME_HEIST),
+        make_vtable<JumperGame>(GAME_JUMPER),
         make_vtable<LeaperGame>(GAME_LEAPER),
         make_vtable<MazeGame>(GAME_MAZE),
         make_vtable<MinerGame>(GAME_MINER),
         make_vtable<Ninja>(GAME_NINJA),
         make_vtable<PlunderGame>(GAME_PLUNDER),
+        make_vtable<StarpilotGame>(GAME_STARPILOT),
     };
     for (const auto &g : table)
         if (name == g.name)

@@ -48,6 +48,8 @@ def hostsim_lib(asset_pack):
 def product_lib():
     from procgen_b200 import build as B
 
-    if not os.path.exists(B.LIB_PATH):
+    # in the dev container (reference tree present) keep the in-tree library in step with the
+    # sources; on the GPU box use the library that travelled with the snapshot
+    if not os.path.exists(B.LIB_PATH) or (os.path.isdir("/root/reference") and B.needs_build()):
         B.build_library()
     return B.LIB_PATH

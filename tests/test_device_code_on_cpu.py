@@ -29,6 +29,15 @@ CASES = [
     ("ninja", "easy", 16, 300),
     ("fruitbot", "hard", 16, 400),  # vertically tiled background, tiled barriers and doors
     ("fruitbot", "easy", 16, 300),
+    ("caveflyer", "hard", 16, 400),  # cave automaton, free rotation (atan2f), lasers
+    ("caveflyer", "memory", 8, 300),
+    ("bossfight", "hard", 16, 500),  # hundreds of spinning bullets and trails
+    ("bossfight", "easy", 8, 300),
+    ("dodgeball", "hard", 16, 400),  # room splitting, lava walls tiled along their length
+    ("dodgeball", "extreme", 8, 300),
+    ("dodgeball", "memory", 8, 300),
+    ("starpilot", "hard", 16, 700),  # std::sort tie order, scrolling tiled background, finish line at t=500
+    ("starpilot", "extreme", 8, 300),
 ]
 
 
@@ -38,6 +47,21 @@ def test_lockstep_bit_exact(ref_lib, hostsim_lib, name, mode, n, steps):
     run_lockstep(ref, dut, steps)
     ref.close()
     dut.close()
+
+
+@pytest.mark.parametrize("prog", ["stdsort_check", "atan2f_check"])
+def test_native_restatements_match_host_libraries(prog, tmp_path):
+    """pg_stdsort.cuh against libstdc++'s std::sort (tie order, heapsort fallback) and pg_atan2f
+    against libm's atan2f: the oracle links both libraries, the device cannot."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / prog)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(root, "procgen_b200", "csrc"),
+                           os.path.join(root, "tests", "native", prog + ".cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout[-2000:]
 
 
 def test_unrestricted_levels_and_other_seed(ref_lib, hostsim_lib):

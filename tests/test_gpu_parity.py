@@ -29,6 +29,12 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     ("climber", "hard", 32, 600),
     ("ninja", "hard", 32, 800),
     ("fruitbot", "hard", 32, 600),
+    ("caveflyer", "hard", 32, 600),
+    ("bossfight", "hard", 32, 800),
+    ("dodgeball", "hard", 32, 600),
+    ("dodgeball", "memory", 16, 400),
+    ("starpilot", "hard", 32, 800),
+    ("starpilot", "extreme", 16, 400),
 ])
 def test_libenv_host_buffers_bit_exact(ref_lib, product_lib, name, mode, n, steps):
     ref, dut = make_pair(product_lib, n, name, distribution_mode=mode, num_levels=200, start_level=0, rand_seed=0)
