@@ -11,7 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle.ref_env import RefVecEnv, mt19937_actions  # noqa: E402
 
-CASES = [("coinrun", "easy", 8, 96), ("coinrun", "hard", 8, 96), ("bigfish", "hard", 8, 96), ("maze", "hard", 8, 96), ("heist", "hard", 8, 96)]
+CASES = [("coinrun", "easy", 8, 96), ("coinrun", "hard", 8, 96), ("bigfish", "hard", 8, 96), ("maze", "hard", 8, 96), ("heist", "hard", 8, 96),
+         ("bossfight", "hard", 8, 96), ("caveflyer", "hard", 8, 96), ("chaser", "hard", 8, 96), ("climber", "hard", 8, 96),
+         ("dodgeball", "hard", 8, 96), ("fruitbot", "hard", 8, 96), ("jumper", "hard", 8, 96), ("jumper", "easy", 8, 96),
+         ("leaper", "hard", 8, 96), ("miner", "hard", 8, 96), ("ninja", "hard", 8, 96), ("plunder", "hard", 8, 96),
+         ("starpilot", "hard", 8, 96), ("maze", "memory", 4, 64), ("dodgeball", "extreme", 4, 64)]
 
 
 def main():

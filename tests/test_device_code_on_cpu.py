@@ -38,6 +38,9 @@ CASES = [
     ("dodgeball", "memory", 8, 300),
     ("starpilot", "hard", 16, 700),  # std::sort tie order, scrolling tiled background, finish line at t=500
     ("starpilot", "extreme", 8, 300),
+    ("jumper", "hard", 16, 400),     # maze + cave generators, compass (ellipse, cosmetic line, bar)
+    ("jumper", "easy", 16, 300),     # compass disc on a non-integer rect
+    ("jumper", "memory", 8, 300),
 ]
 
 

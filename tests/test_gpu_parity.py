@@ -35,6 +35,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     ("dodgeball", "memory", 16, 400),
     ("starpilot", "hard", 32, 800),
     ("starpilot", "extreme", 16, 400),
+    ("jumper", "hard", 32, 600),
+    ("jumper", "easy", 32, 600),
 ])
 def test_libenv_host_buffers_bit_exact(ref_lib, product_lib, name, mode, n, steps):
     ref, dut = make_pair(product_lib, n, name, distribution_mode=mode, num_levels=200, start_level=0, rand_seed=0)

@@ -69,7 +69,8 @@ def test_oracle_reproduces_golden(ref_lib, asset_pack, fixture):
 
 def test_raster_restatement_matches_real_qt6(ref_lib, asset_pack):
     """The CPU raster restatement vs a REAL Qt raster engine (Qt 6.6.3 shipped with Nsight Compute):
-    zero differing pixels for the un-rotated draw paths of coinrun / bigfish / maze."""
+    zero differing pixels for the un-rotated draw paths (scaled blits, tiling, fillRect) and for
+    jumper's compass (drawEllipse, drawLine)."""
     from oracle import build_ref, qt6_support
     from oracle.ref_env import REF_LIB_QT6
 
@@ -79,7 +80,8 @@ def test_raster_restatement_matches_real_qt6(ref_lib, asset_pack):
         if not build_ref.reference_available():
             pytest.skip("libenv_ref_qt6.so not built and reference tree absent")
         build_ref.build(qt6=True)
-    for name, mode in [("coinrun", "hard"), ("bigfish", "hard"), ("maze", "hard")]:
+    for name, mode in [("coinrun", "hard"), ("bigfish", "hard"), ("maze", "hard"), ("jumper", "easy"), ("jumper", "hard"),
+                       ("fruitbot", "hard"), ("starpilot", "hard")]:
         n, steps = 8, 150
         a = RefVecEnv(n, name, distribution_mode=mode, num_levels=0, rand_seed=3)
         b = RefVecEnv(n, name, distribution_mode=mode, num_levels=0, rand_seed=3, lib_path=REF_LIB_QT6)
@@ -119,3 +121,96 @@ def test_rotated_raster_restatement_close_to_real_qt6(ref_lib, asset_pack):
     a.close()
     b.close()
     assert bad <= 1e-5 * tot, f"{bad} of {tot} pixels differ from Qt 6.6.3"
+
+
+def _qt6_pair():
+    import ctypes as C
+
+    from oracle import qt6_support
+    from oracle.ref_env import REF_LIB, REF_LIB_QT6
+
+    if not qt6_support.available() or not os.path.exists(REF_LIB_QT6):
+        pytest.skip("Qt 6 backend not available")
+    return C.CDLL(REF_LIB), C.CDLL(REF_LIB_QT6, handle=qt6_support.lazy_dlopen(REF_LIB_QT6))
+
+
+def test_ellipse_and_line_restatement_match_real_qt6(ref_lib, asset_pack):
+    """drawEllipse (midpoint algorithm on integer rects, pen / no pen / translucent brush, clipped by
+    the device edge) and drawLine(int...) with a cosmetic pen: every case identical to Qt 6.6.3."""
+    import ctypes as C
+
+    mine, qt = _qt6_pair()
+    bg = 0xff102030
+
+    def ell(lib, x, y, w, h, col, pw):
+        dst = np.full((64, 64), bg, np.uint32)
+        lib.shim_test_draw_ellipse(dst.ctypes.data_as(C.c_void_p), 64, 64, C.c_double(x), C.c_double(y), C.c_double(w), C.c_double(h), *col, pw)
+        return dst
+
+    def line(lib, x1, y1, x2, y2, pw):
+        dst = np.full((64, 64), bg, np.uint32)
+        lib.shim_test_draw_line(dst.ctypes.data_as(C.c_void_p), 64, 64, x1, y1, x2, y2, 252, 186, 3, pw)
+        return dst
+
+    for x in range(-3, 60, 9):
+        for y in range(-3, 60, 11):
+            for w in range(1, 20, 2):
+                for h in (1, 2, 3, 8, 16, w):
+                    for col, pw in (((168, 166, 158, 255), 1), ((255, 255, 255, 120), -1), ((252, 186, 3, 255), 0)):
+                        assert np.array_equal(ell(mine, x, y, w, h, col, pw), ell(qt, x, y, w, h, col, pw)), (x, y, w, h, col, pw)
+    # jumper's two compass discs (jumper.cpp:138-141): easy mode's sits on a non-integer rect
+    unit = np.float32(64) / np.float32(12)
+    easy = (float(np.float32(8.75) * unit), float(np.float32(.25) * unit), float(np.float32(3) * unit))
+    for rect in ((easy[0], easy[1], easy[2], easy[2]), (55.0, 1.0, 8.0, 8.0)):
+        assert np.array_equal(ell(mine, *rect, (168, 166, 158, 255), 1), ell(qt, *rect, (168, 166, 158, 255), 1)), rect
+    # every needle the compass can draw and more: all integer offsets within 9 px of in-bounds centres
+    for cx, cy in ((54, 9), (59, 5), (20, 40), (10, 10)):
+        for dx in range(-9, 10):
+            for dy in range(-9, 10):
+                if not (0 <= cx + dx < 64 and 0 <= cy + dy < 64):
+                    continue
+                for pw in (0, 1):
+                    assert np.array_equal(line(mine, cx, cy, cx + dx, cy + dy, pw), line(qt, cx, cy, cx + dx, cy + dy, pw)), (cx, cy, dx, dy, pw)
+
+
+def test_scaled_blit_and_fill_sweep_match_real_qt6(ref_lib, asset_pack):
+    """Rules S and F on random rects, with positions and sizes deliberately placed on exact halves
+    and quarters (qRound ties; Qt 6 rounds negative ties away from zero)."""
+    import ctypes as C
+
+    mine, qt = _qt6_pair()
+    rng = np.random.RandomState(7)
+    srcs = [(np.arange(sw * sh, dtype=np.uint32).reshape(sh, sw)) | 0xff000000 for sw, sh in ((8, 8), (64, 64), (17, 17), (480, 270), (128, 64))]
+
+    def draw(lib, src, x, y, w, h):
+        sh, sw = src.shape
+        dst = np.zeros((64, 64), np.uint32)
+        lib.shim_test_draw_image(dst.ctypes.data_as(C.c_void_p), 64, 64, src.ctypes.data_as(C.c_void_p), sw, sh, 0, C.c_double(x), C.c_double(y),
+                                 C.c_double(w), C.c_double(h), C.c_double(0), C.c_double(1.0), 0)
+        return dst
+
+    def fill(lib, x, y, w, h):
+        dst = np.zeros((64, 64), np.uint32)
+        lib.shim_test_fill_rect(dst.ctypes.data_as(C.c_void_p), 64, 64, C.c_double(x), C.c_double(y), C.c_double(w), C.c_double(h), 200, 100, 50)
+        return dst
+
+    def rnd():
+        k = rng.randint(4)
+        if k == 0:
+            return float(rng.randint(-40, 100)) / 2
+        if k == 1:
+            return float(rng.randint(-80, 200)) / 4
+        return rng.uniform(-20, 70)
+
+    for _ in range(1500):
+        x, y = rnd(), rnd()
+        w = abs(rnd()) + 0.1 if rng.randint(2) else float(rng.randint(1, 80)) / 2
+        h = abs(rnd()) + 0.1 if rng.randint(2) else float(rng.randint(1, 80)) / 2
+        if rng.randint(3) == 0:
+            w *= 4
+            h *= 4
+        src = srcs[rng.randint(len(srcs))]
+        if w == src.shape[1] and h == src.shape[0]:
+            continue  # 1:1 draws take Qt's unscaled path, which no in-scope draw call reaches
+        assert np.array_equal(draw(mine, src, x, y, w, h), draw(qt, src, x, y, w, h)), (x, y, w, h, src.shape)
+        assert np.array_equal(fill(mine, x, y, w, h), fill(qt, x, y, w, h)), (x, y, w, h)
