@@ -126,6 +126,17 @@ LIBENV_API void libenv_act(libenv_env *handle);
 /* vecgame.cpp:95-98 */
 LIBENV_API void libenv_close(libenv_env *handle);
 
+/* State snapshots — replaces get_state / set_state, src/vecgame.cpp:437-457 (declared to cffi at
+ * procgen/env.py:132-135). The blob is the reference's own wire format, byte for byte
+ * (Game::serialize game.cpp:170-229, BasicAbstractGame::serialize basic-abstract-game.cpp:1169-1223,
+ * Entity::serialize entity.cpp:90-131, RandGen::serialize randgen.cpp:100-107, per-game tails): a
+ * state saved by the reference loads here and vice versa. get_state returns the number of bytes
+ * written (a too small buffer is fatal, like the reference's fassert); set_state also re-renders
+ * the env's observation and rewrites its rew / first / info slots from the restored state (Game::observe).
+ * Both wait for the step in flight. */
+LIBENV_API int get_state(libenv_env *handle, int env_idx, char *data, int length);
+LIBENV_API void set_state(libenv_env *handle, int env_idx, char *data, int length);
+
 /* ------------------------------------------------------------------ Part 2: device-resident */
 
 struct pgb200_device_buffers {
@@ -175,6 +186,14 @@ LIBENV_API int pgb200_debug_read_env(libenv_env *handle, int env, void *hdr_out,
 
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 LIBENV_API int64_t pgb200_kernel_launches(libenv_env *handle);
+
+/* Per-kernel device timing for measurement (bench.py roofline): between begin and end every
+ * (logic_kernel, render_kernel) launch pair is bracketed by CUDA events on the stream it runs on.
+ * end() synchronises and writes out[0] = sum of logic-kernel ms, out[1] = sum of render-kernel ms,
+ * out[2] = number of launch pairs timed, out[3] = env-steps those launches processed; returns the
+ * number of pairs. At most max_launch_pairs pairs are timed (further launches run untimed). */
+LIBENV_API int pgb200_kernel_timing_begin(libenv_env *handle, int max_launch_pairs);
+LIBENV_API int pgb200_kernel_timing_end(libenv_env *handle, double *out);
 
 /* 1 if this library was built for the GPU (the product), 0 for the CPU debug harness in tests/. */
 LIBENV_API int pgb200_is_device_build(void);

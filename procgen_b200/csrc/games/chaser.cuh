@@ -76,7 +76,7 @@ struct ChaserGame : Defaults<ChaserGame>, DrawDefaults<ChaserGame> {
     template <class Frame>
     static PG_HD bool make_grid_obj_blit(Ctx &c, const Frame &f, Blit &b, double *rect, int type, int theme) {
         if (type != ORB)
-            return false;
+            return DrawDefaults<ChaserGame>::make_grid_obj_blit(c, f, b, rect, type, theme);
         double x = rect[0] + rect[2] * (double)(1 - ORB_DIM) / 2;
         double y = rect[1] + rect[3] * (double)(1 - ORB_DIM) / 2;
         make_solid_blit(b, x, y, rect[2] * (double)ORB_DIM, rect[3] * (double)ORB_DIM, (0u << 16) | (255u << 8) | 0u);

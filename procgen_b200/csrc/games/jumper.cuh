@@ -89,7 +89,6 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
     static PG_HD void make_overlay_blits(Ctx &c, Frame &f) {
         EnvHdr &h = *c.h;
         JumperState &s = st(c);
-        f.n_overlay = 0;
         if (h.options.distribution_mode == MemoryMode)
             return;
         const Entity &a = agent_of(c);
@@ -98,7 +97,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         Raster<JumperGame, Frame>::abs_rect(f.cam, (float)((double)(h.view_dim - s.compass_dim) - .25), .25, s.compass_dim, s.compass_dim, cr_);
         const uint32_t clock_color = (168u << 16) | (166u << 8) | 158u;
         const uint32_t highlight = (252u << 16) | (186u << 8) | 3u;
-        int n = 0;
+        int n = f.n_overlay;
         bool ok = make_ellipse_blit(f, f.overlay[n++], 0, cr_[0], cr_[1], cr_[2], cr_[3], 0xff000000u | clock_color, true);
         // QRectF::center() = x + w/2 in double, narrowed to float (jumper.cpp:146-148)
         float cx = (float)(cr_[0] + cr_[2] / 2);

@@ -110,8 +110,7 @@ struct Ninja : Defaults<Ninja>, DrawDefaults<Ninja> {
         float bar_height = 3 * st(c).jump_charge;
         double r[4];
         Raster<Ninja, Frame>::abs_rect(f.cam, .25, (float)((double)c.h->visibility - .5 - (double)bar_height), .5, bar_height, r);
-        make_solid_blit(f.overlay[0], r[0], r[1], r[2], r[3], (66u << 16) | (245u << 8) | 135u);
-        f.n_overlay = 1;
+        make_solid_blit(f.overlay[f.n_overlay++], r[0], r[1], r[2], r[3], (66u << 16) | (245u << 8) | 135u);
     }
     static PG_HD void fill_ground_block(Ctx &c, int x, int y, int dx, int dy) {
         if (dy <= 0)

@@ -48,10 +48,9 @@ struct PlunderGame : Defaults<PlunderGame>, DrawDefaults<PlunderGame> {
         PlunderState &s = st(c);
         double r[4];
         Raster<PlunderGame, Frame>::abs_rect(f.cam, .25, .25, h.main_width * s.juice_left, .5, r);
-        make_solid_blit(f.overlay[0], r[0], r[1], r[2], r[3], (66u << 16) | (245u << 8) | 135u);
+        make_solid_blit(f.overlay[f.n_overlay++], r[0], r[1], r[2], r[3], (66u << 16) | (245u << 8) | 135u);
         Raster<PlunderGame, Frame>::abs_rect(f.cam, .25, .75, (float)(h.main_width * (s.targets_hit * 1.0 / s.target_quota)), .5, r);
-        make_solid_blit(f.overlay[1], r[0], r[1], r[2], r[3], (245u << 16) | (66u << 8) | 144u);
-        f.n_overlay = 2;
+        make_solid_blit(f.overlay[f.n_overlay++], r[0], r[1], r[2], r[3], (245u << 16) | (66u << 8) | 144u);
     }
     static PG_HD bool should_preserve_type_themes(Ctx &c, int type) { return type == SHIP; }
     // plunder.cpp:87-110

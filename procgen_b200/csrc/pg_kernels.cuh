@@ -35,6 +35,7 @@ struct KParams {
     Options options;
     int32_t level_seed_low, level_seed_high;
     int32_t game_id;
+    int32_t fixed_asset_seed;   // FNV-1a of the game name (vecgame.cpp:156-167, 324-327)
     int32_t snap;
     int32_t env_global_offset;  // game_n = env_global_offset + env
     uint32_t *dbg_cycles;       // optional [N] per-env logic duration in SM cycles (profiling aid)
@@ -75,6 +76,7 @@ PG_HD void env_init_logic(const KParams &p, int env) {
     EnvHdr &h = *c.h;
     h.options = p.options;
     h.game_id = p.game_id;
+    h.fixed_asset_seed = p.fixed_asset_seed;
     h.game_n = p.env_global_offset + env;
     h.level_seed_low = p.level_seed_low;
     h.level_seed_high = p.level_seed_high;

@@ -1053,7 +1053,22 @@ struct Raster {
                 h.err |= ERR_BLIT_OVERFLOW;
             if (h.options.use_backgrounds)
                 G::make_background_blits(c, f);
-            G::make_overlay_blits(c, f);
+            if (h.has_useful_vel_info && h.options.paint_vel_info) {
+                // draw_foreground's last step (basic-abstract-game.cpp:960-969): two grey squares
+                // whose shade encodes the agent's velocity; to_shade is qt-utils.h:21-28
+                const Entity &a = agent_of(c);
+                const float infodim = (float)(RES_H * .2);
+                float f1 = (float)(.5 * (double)a.vx / (double)h.maxspeed + .5);
+                float f2 = (float)(.5 * (double)a.vy / (double)h.max_jump + .5);
+                int s1 = (int)(f1 * 255), s2 = (int)(f2 * 255);
+                s1 = s1 < 0 ? 0 : (s1 > 255 ? 255 : s1);
+                s2 = s2 < 0 ? 0 : (s2 > 255 ? 255 : s2);
+                make_solid_blit(f.overlay[0], 0, 0, (double)infodim, (double)infodim, ((uint32_t)s1 << 16) | ((uint32_t)s1 << 8) | (uint32_t)s1);
+                make_solid_blit(f.overlay[1], (double)infodim, 0, (double)infodim, (double)infodim,
+                                ((uint32_t)s2 << 16) | ((uint32_t)s2 << 8) | (uint32_t)s2);
+                f.n_overlay = 2;
+            }
+            G::make_overlay_blits(c, f);  // game overlays are appended after the velocity squares
         }
         // columns by threads 0.., rows by threads from the top end so they land on other lanes
         for (int i = tid; i < nx; i += nthreads) {
@@ -1377,11 +1392,30 @@ struct DrawDefaults {
         make_image_blit(f.bg[0], main_rect[0], main_rect[1], main_rect[2], main_rect[3], bg, false, 256, f.snap != 0);
         f.n_bg = 1;
     }
+    // game_draw overrides that paint after draw_foreground: append at f.overlay[f.n_overlay...]
     template <class Frame>
     static PG_HD void make_overlay_blits(Ctx &c, Frame &f) {}
-    // draw_grid_obj for types >= 100 (chaser overrides); false = nothing known to draw
+    // draw_grid_obj (basic-abstract-game.cpp:915-919): a fillRect in color_for_type's colour
+    // (:455-481) — defined only in monochrome mode; false = the reference would fassert
     template <class Frame>
-    static PG_HD bool make_grid_obj_blit(Ctx &c, const Frame &f, Blit &b, double *rect, int type, int theme) { return false; }
+    static PG_HD bool make_grid_obj_blit(Ctx &c, const Frame &f, Blit &b, double *rect, int type, int theme) {
+        if (!c.h->options.use_monochrome_assets)
+            return false;
+        if (c.h->options.restrict_themes && !G::should_preserve_type_themes(c, type))
+            theme = 0;
+        const int k = 4;
+        const int kcubed = k * k * k;
+        const int chunk = 256 / k;
+        if (type >= kcubed)
+            return false;
+        int new_type = (29 * (type + 1)) % kcubed;
+        new_type = (new_type + 19 * theme) % kcubed;
+        const uint32_t r = (uint32_t)(chunk * (new_type / (k * k) + 1) - 1);
+        const uint32_t g = (uint32_t)(chunk * ((new_type / k) % k + 1) - 1);
+        const uint32_t bl = (uint32_t)(chunk * (new_type % k + 1) - 1);
+        make_solid_blit(b, rect[0], rect[1], rect[2], rect[3], (r << 16) | (g << 8) | bl);
+        return true;
+    }
 };
 
 }  // namespace pg

@@ -37,6 +37,7 @@
 #include "games/ninja.cuh"
 #include "games/plunder.cuh"
 #include "games/starpilot.cuh"
+#include "pg_state_io.h"
 
 #ifndef PG_HOSTSIM
 #include <cuda_runtime.h>
@@ -192,11 +193,26 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(KParams p) {
 }
 #endif
 
+#ifndef PG_HOSTSIM
+// Game::observe without a step (set_state, vecgame.cpp:454-456): camera, then the render kernel
+template <class G>
+__global__ void camera_kernel(KParams p) {
+    using Frame = typename FrameFor<G>::type;
+    if (threadIdx.x == 0 && blockIdx.x < (unsigned)p.env_count) {
+        const int env = p.env_first + (int)blockIdx.x * p.env_step;
+        Ctx c = make_ctx(p, env);
+        Raster<G, Frame>::prepare_camera(c);
+        write_step_outputs(p, env, *c.h);  // Game::observe's scalar stores, game.cpp:160-164
+    }
+}
+#endif
+
 struct LaunchCtx {
 #ifndef PG_HOSTSIM
     cudaStream_t stream;
     unsigned int *ticket;     // work counter of this launch slot (one per in-flight logic kernel)
     int max_logic_blocks;     // SM count x resident CTAs per SM
+    cudaEvent_t *tev;         // optional: 3 events (before logic, between, after render) for kernel timing
 #endif
     int64_t *launch_counter;
 };
@@ -216,8 +232,14 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     if (logic_blocks > lc.max_logic_blocks)
         logic_blocks = lc.max_logic_blocks;
     CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, sizeof(unsigned int), lc.stream));
+    if (lc.tev)
+        CUDA_CHECK(cudaEventRecord(lc.tev[0], lc.stream));
     logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, lc.stream>>>(p, lc.ticket);
+    if (lc.tev)
+        CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
     render_kernel<G><<<p.env_count, kRenderThreads, sizeof(Frame), lc.stream>>>(p);
+    if (lc.tev)
+        CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
     CUDA_CHECK(cudaGetLastError());
     (*lc.launch_counter) += 2;
 #else
@@ -237,17 +259,45 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
 #endif
 }
 
+template <class G>
+void launch_observe_only(const KParams &p, const LaunchCtx &lc) {
+    using Frame = typename FrameFor<G>::type;
+    if (p.env_count <= 0)
+        return;
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Frame)));
+    camera_kernel<G><<<p.env_count, 32, 0, lc.stream>>>(p);
+    render_kernel<G><<<p.env_count, kRenderThreads, sizeof(Frame), lc.stream>>>(p);
+    CUDA_CHECK(cudaGetLastError());
+#else
+    static thread_local Frame *f = new Frame;
+    for (int b = 0; b < p.env_count; b++) {
+        int env = p.env_first + b * p.env_step;
+        Ctx c = make_ctx(p, env);
+        Raster<G, Frame>::prepare_camera(c);
+        write_step_outputs(p, env, *c.h);
+        env_render_begin<G, Frame>(p, env, *f, 0, 1);
+        env_render_build<G, Frame>(p, env, *f, 0, 1, 1);
+        env_render_masks<G, Frame>(p, env, *f, 0, 1);
+        for (int quad = 0; quad < kQuads; quad++) env_render_quad<G, Frame>(p, env, *f, quad);
+    }
+#endif
+    (*lc.launch_counter) += 2;
+}
+
 struct GameVTable {
     const char *name;
     int id;
     int ent_cap, grid_cap, scratch_words;
     void (*init)(const KParams &, const LaunchCtx &);
     void (*step)(const KParams &, const LaunchCtx &);
+    void (*observe_only)(const KParams &, const LaunchCtx &);
 };
 
 template <class G>
 GameVTable make_vtable(int id) {
-    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, &launch_env_kernel<G, true>, &launch_env_kernel<G, false>};
+    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, &launch_env_kernel<G, true>, &launch_env_kernel<G, false>,
+                      &launch_observe_only<G>};
 }
 
 const GameVTable *find_game(const std::string &name) {
@@ -305,6 +355,16 @@ void copy_to_dev(void *dst, const void *src, size_t bytes) {
 #endif
 }
 
+// vecgame.cpp:156-167: system-independent hash of the game name
+static int32_t fnv1a(const char *str) {
+    uint32_t hash = 0x811c9dc5u;
+    for (const char *c = str; *c; c++) {
+        hash ^= (uint8_t)*c;
+        hash *= 0x1000193u;
+    }
+    return (int32_t)hash;
+}
+
 // ================================================================= VecEnv (VecGame, vecgame.h)
 struct VecEnv {
     int num_envs = 0;
@@ -320,6 +380,7 @@ struct VecEnv {
     int32_t *d_action = nullptr;
     bool initial_reset_done = false;
     int64_t launches = 0;
+    host::ConstGameFields const_fields;  // options Game::serialize writes but no kernel reads
 
 #ifndef PG_HOSTSIM
     cudaStream_t stream = nullptr;
@@ -328,6 +389,11 @@ struct VecEnv {
     cudaStream_t aux[kAuxStreams] = {};
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[kAuxStreams] = {};
+    // optional per-launch kernel timing (pgb200_kernel_timing_begin/end): a pool of event triples
+    std::vector<cudaEvent_t> tev_pool;
+    std::vector<int> tev_envs;   // env count of each timed launch pair
+    size_t tev_used = 0;
+    bool timing = false;
 #endif
     static constexpr int kChunks = PG_STEP_CHUNKS;
     static constexpr int kMaxTickets = 64;
@@ -356,6 +422,7 @@ struct VecEnv {
         lc.stream = stream;
         lc.ticket = d_tickets;
         lc.max_logic_blocks = max_logic_blocks;
+        lc.tev = nullptr;
 #endif
         lc.launch_counter = &launches;
         return lc;
@@ -386,6 +453,7 @@ struct VecEnv {
                 KParams p = base;
                 p.assets = d_assets[g];
                 p.game_id = games[g]->id;
+                p.fixed_asset_seed = fnv1a(games[g]->name);
                 p.env_first = g + lo * G;
                 p.env_step = G;
                 p.env_count = hi - lo;
@@ -394,6 +462,11 @@ struct VecEnv {
                 if (nstreams)
                     lc.stream = aux[k % nstreams];
                 lc.ticket = d_tickets + (k % kMaxTickets);
+                if (timing && tev_used + 3 <= tev_pool.size()) {
+                    lc.tev = &tev_pool[tev_used];
+                    tev_used += 3;
+                    tev_envs.push_back(p.env_count);
+                }
 #endif
                 if (init)
                     games[g]->init(p, lc);
@@ -559,8 +632,6 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     opts.ensure_empty();
     if (use_generated_assets)
         pg_fatal("use_generated_assets is not supported by procgen_b200\n");
-    if (use_monochrome_assets || paint_vel_info)
-        pg_fatal("use_monochrome_assets / paint_vel_info are not supported by procgen_b200 yet\n");
 
     std::vector<std::string> env_names = split(env_name, ",");
     const int G = (int)env_names.size();
@@ -570,6 +641,10 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
         const GameVTable *g = find_game(name);
         if (!g)
             pg_fatal("unknown or not yet supported env_name '%s'\n", name.c_str());
+        // These five games honour center_agent=false by drawing their whole (up to 64x64-cell)
+        // world; the render kernel's per-frame cell window is sized for the default centred view.
+        if (!center_agent && (name == "coinrun" || name == "climber" || name == "caveflyer" || name == "jumper" || name == "ninja"))
+            pg_fatal("center_agent=false is not supported for '%s' by procgen_b200 yet\n", name.c_str());
         // mode validity, game.cpp:56-66
         if (dist_mode == EasyMode || dist_mode == HardMode) {
         } else if (dist_mode == ExtremeMode) {
@@ -693,6 +768,10 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     p.options.center_agent = center_agent;
     p.options.use_sequential_levels = use_sequential_levels;
     p.options.debug_mode = debug_mode;
+    v->const_fields.use_easy_jump = use_easy_jump;
+    v->const_fields.plain_assets = plain_assets;
+    v->const_fields.physics_mode = physics_mode;
+    v->const_fields.game_type = game_type;
     p.options.distribution_mode = dist_mode;
     p.snap = snap ? 1 : 0;
     p.env_global_offset = env_index_offset;
@@ -991,6 +1070,136 @@ int pgb200_debug_read_env(libenv_env *handle, int env, void *hdr_out, void *ents
     return hdr.n_ents;
 }
 
+// ---- get_state / set_state (vecgame.cpp:437-457)
+static void copy_from_dev(void *dst, const void *src, size_t bytes) {
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
+
+static void fetch_env(VecEnv *v, int env, host::HostEnv &e) {
+    const KParams &p = v->base;
+    e.ent_cap = p.ent_stride - 1;
+    e.ents.resize((size_t)p.ent_stride);
+    e.grid.resize((size_t)p.grid_stride);
+    e.scratch.resize((size_t)p.scratch_stride);
+    copy_from_dev(&e.h, p.hdr + env, sizeof(EnvHdr));
+    copy_from_dev(e.ents.data(), p.ents + (size_t)env * p.ent_stride, e.ents.size() * sizeof(Entity));
+    copy_from_dev(e.grid.data(), p.grid + (size_t)env * p.grid_stride, e.grid.size() * sizeof(int16_t));
+    copy_from_dev(&e.rng, p.rng + env, sizeof(MT19937));
+    copy_from_dev(&e.lvl_rng, p.lvl_rng + env, sizeof(MT19937));
+    if (!e.scratch.empty())
+        copy_from_dev(e.scratch.data(), p.scratch + (size_t)env * p.scratch_stride, e.scratch.size() * sizeof(int32_t));
+}
+
+static void store_env(VecEnv *v, int env, const host::HostEnv &e) {
+    const KParams &p = v->base;
+    copy_to_dev(p.hdr + env, &e.h, sizeof(EnvHdr));
+    copy_to_dev(p.ents + (size_t)env * p.ent_stride, e.ents.data(), e.ents.size() * sizeof(Entity));
+    copy_to_dev(p.grid + (size_t)env * p.grid_stride, e.grid.data(), e.grid.size() * sizeof(int16_t));
+    copy_to_dev(p.rng + env, &e.rng, sizeof(MT19937));
+    copy_to_dev(p.lvl_rng + env, &e.lvl_rng, sizeof(MT19937));
+    if (!e.scratch.empty())
+        copy_to_dev(p.scratch + (size_t)env * p.scratch_stride, e.scratch.data(), e.scratch.size() * sizeof(int32_t));
+}
+
+int get_state(libenv_env *handle, int env_idx, char *data, int length) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    pg_fassert(env_idx >= 0 && env_idx < v->num_envs);
+    v->ensure_initial_reset();
+    v->sync();  // wait_for_stepping_threads
+    host::HostEnv e;
+    fetch_env(v, env_idx, e);
+    const GameVTable *g = v->games[(size_t)env_idx % v->games.size()];
+    try {
+        host::WriteBuf b(data, (size_t)(length < 0 ? 0 : length));
+        host::serialize_env(g->name, g->id, e, v->const_fields, b);
+        return (int)b.offset;
+    } catch (const std::exception &ex) {
+        pg_fatal("get_state: %s\n", ex.what());
+    }
+    return 0;
+}
+
+void set_state(libenv_env *handle, int env_idx, char *data, int length) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    pg_fassert(env_idx >= 0 && env_idx < v->num_envs);
+    v->ensure_initial_reset();
+    v->sync();
+    host::HostEnv e;
+    fetch_env(v, env_idx, e);  // capacities, game id and the fields the blob does not carry
+    const size_t gi = (size_t)env_idx % v->games.size();
+    const GameVTable *g = v->games[gi];
+    try {
+        host::ReadBuf b(data, (size_t)(length < 0 ? 0 : length));
+        host::deserialize_env(g->name, g->id, e, b);
+    } catch (const std::exception &ex) {
+        pg_fatal("set_state: %s\n", ex.what());
+    }
+    store_env(v, env_idx, e);
+    // Game::observe(): re-render this env and rewrite its rew / first / info slots from the restored step_data
+    KParams p = v->base;
+    p.assets = v->d_assets[gi];
+    p.game_id = g->id;
+    p.env_first = env_idx;
+    p.env_step = 1;
+    p.env_count = 1;
+    LaunchCtx lc = v->lctx();
+    g->observe_only(p, lc);
+    v->sync();
+}
+
 int64_t pgb200_kernel_launches(libenv_env *handle) { return ((VecEnv *)handle)->launches; }
+
+int pgb200_kernel_timing_begin(libenv_env *handle, int max_launch_pairs) {
+#ifndef PG_HOSTSIM
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+    while ((int)v->tev_pool.size() < 3 * max_launch_pairs) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreate(&e));
+        v->tev_pool.push_back(e);
+    }
+    v->tev_used = 0;
+    v->tev_envs.clear();
+    v->timing = true;
+    return 0;
+#else
+    return -1;
+#endif
+}
+
+int pgb200_kernel_timing_end(libenv_env *handle, double *out) {
+#ifndef PG_HOSTSIM
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+    v->timing = false;
+    double logic_ms = 0, render_ms = 0, envs = 0;
+    const int pairs = (int)(v->tev_used / 3);
+    for (int i = 0; i < pairs; i++) {
+        float a = 0, b = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&a, v->tev_pool[3 * i], v->tev_pool[3 * i + 1]));
+        CUDA_CHECK(cudaEventElapsedTime(&b, v->tev_pool[3 * i + 1], v->tev_pool[3 * i + 2]));
+        logic_ms += a;
+        render_ms += b;
+        envs += v->tev_envs[i];
+    }
+    out[0] = logic_ms;
+    out[1] = render_ms;
+    out[2] = pairs;
+    out[3] = envs;
+    v->tev_used = 0;
+    v->tev_envs.clear();
+    return pairs;
+#else
+    return -1;
+#endif
+}
 
 }  // extern "C"

@@ -246,10 +246,21 @@ class BaseProcgenEnv:
         return getattr(self, method)(*args, **kwargs)
 
     def get_state(self):
-        raise NotImplementedError("get_state/set_state wire format: SURVEY §8(f) item 1, not built yet")
+        """One bytes blob per env in the reference's wire format (env.py:139-147, vecgame.cpp:437-445)."""
+        import ctypes as C
+
+        buf = C.create_string_buffer(MAX_STATE_SIZE)
+        out = []
+        for i in range(self.num):
+            n = int(self._lib.get_state(self._h, i, buf, MAX_STATE_SIZE))
+            out.append(bytes(buf.raw[:n]))
+        return out
 
     def set_state(self, states):
-        raise NotImplementedError("get_state/set_state wire format: SURVEY §8(f) item 1, not built yet")
+        """Load one blob per env (env.py:149-153, vecgame.cpp:447-457); observations and info are refreshed."""
+        assert len(states) == self.num
+        for i, st in enumerate(states):
+            self._lib.set_state(self._h, i, st, len(st))
 
     def get_combos(self):  # env.py:155-172
         return [("LEFT", "DOWN"), ("LEFT",), ("LEFT", "UP"), ("DOWN",), (), ("UP",), ("RIGHT", "DOWN"), ("RIGHT",),
@@ -280,6 +291,17 @@ class BaseProcgenEnv:
 
     def kernel_launches(self) -> int:
         return int(self._lib.pgb200_kernel_launches(self._h))
+
+    def kernel_timing_begin(self, max_launch_pairs: int) -> None:
+        """Bracket every (logic, render) kernel pair with CUDA events until kernel_timing_end()."""
+        self._lib.pgb200_kernel_timing_begin(self._h, int(max_launch_pairs))
+
+    def kernel_timing_end(self) -> dict:
+        import ctypes as C
+
+        out = (C.c_double * 4)()
+        pairs = int(self._lib.pgb200_kernel_timing_end(self._h, out))
+        return {"logic_ms": out[0], "render_ms": out[1], "launch_pairs": pairs, "env_steps": out[3]}
 
     def gather_observations(self, dst: int = 0):
         """The only collective on this path: NCCL gather of this rank's rgb shard to `dst`.

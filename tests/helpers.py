@@ -40,3 +40,39 @@ def run_lockstep(ref, dut, steps, seed=0, rgb_tol=0):
         dut.lib.pgb200_get_errors.restype = C.c_uint32
         err = dut.lib.pgb200_get_errors(C.c_void_p(dut.h), None)
         assert err == 0, f"device latched error bits {err:#x} (capacity overflow / unsupported feature)"
+
+
+def run_state_roundtrip(make_ref, make_dut, num, steps, check_every=25):
+    """Full-state parity through the reference's own wire format (vecgame.cpp:437-457), following the
+    shape of the reference's state_test.py: (1) the blobs of both implementations are byte-identical
+    along a lockstep run, (2) reference blobs loaded into FRESH envs of both implementations (built
+    with another seed) give the same frame and info immediately and the same trajectory afterwards,
+    (3) which is also the trajectory the original envs continue on."""
+    ref, dut = make_ref(0), make_dut(0)
+    acts = mt19937_actions(0, num, 2 * steps)
+    for t in range(steps):
+        if t % check_every == 0:
+            for e in range(num):
+                assert ref.get_state(e) == dut.get_state(e), f"step {t} env {e}: state blobs differ"
+        ref.act(acts[t])
+        dut.act(acts[t])
+        ref.observe()
+        dut.observe()
+    blobs = [ref.get_state(e) for e in range(num)]
+    assert blobs == [dut.get_state(e) for e in range(num)]
+    ref2, dut2 = make_ref(5), make_dut(5)
+    for e in range(num):
+        ref2.set_state(e, blobs[e])
+        dut2.set_state(e, blobs[e])
+    assert_same_observation(ref2, dut2, "after set_state")
+    for t in range(steps, 2 * steps):
+        ref.act(acts[t])
+        ref2.act(acts[t])
+        dut2.act(acts[t])
+        assert_same_observation(ref2, dut2, t)
+        r0, o0, f0 = ref.observe()
+        r2, o2, f2 = ref2.observe()
+        assert np.array_equal(o0["rgb"], o2["rgb"]) and np.array_equal(r0, r2) and np.array_equal(f0, f2)
+    assert [ref2.get_state(e) for e in range(num)] == [dut2.get_state(e) for e in range(num)]
+    for env in (ref, dut, ref2, dut2):
+        env.close()

@@ -4,7 +4,7 @@ lockstep with the oracle through the same libenv C ABI. This is not a product pa
 refuses to load that build, see test_abi.py); the GPU parity tests proper are in test_gpu_parity.py."""
 import pytest
 
-from helpers import make_pair, run_lockstep
+from helpers import make_pair, run_lockstep, run_state_roundtrip
 
 CASES = [
     ("coinrun", "easy", 16, 400),
@@ -65,6 +65,47 @@ def test_native_restatements_match_host_libraries(prog, tmp_path):
                            os.path.join(root, "tests", "native", prog + ".cpp"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout[-2000:]
+
+
+ALL_GAMES = "bigfish,bossfight,caveflyer,chaser,climber,coinrun,dodgeball,fruitbot,heist,jumper,leaper,maze,miner,ninja,plunder,starpilot"
+
+
+def test_sixteen_game_list_bit_exact(ref_lib, hostsim_lib):
+    """BASELINE.json configs[4] shape: env n plays game n % 16 (vecgame.cpp:295-310)."""
+    ref, dut = make_pair(hostsim_lib, 32, ALL_GAMES, distribution_mode="hard", num_levels=200, start_level=0, rand_seed=0)
+    run_lockstep(ref, dut, 300)
+    ref.close()
+    dut.close()
+
+
+@pytest.mark.parametrize("name,extra", [
+    ("coinrun", dict(restrict_themes=True)),
+    ("coinrun", dict(use_backgrounds=False)),
+    ("heist", dict(center_agent=False)),
+    ("maze", dict(use_sequential_levels=True, num_levels=3)),
+    ("plunder", dict(restrict_themes=True, use_backgrounds=False)),
+    ("coinrun", dict(use_monochrome_assets=True, use_backgrounds=False, restrict_themes=True)),
+    ("chaser", dict(use_monochrome_assets=True, use_backgrounds=False)),
+    ("ninja", dict(paint_vel_info=True)),
+    ("jumper", dict(paint_vel_info=True, use_monochrome_assets=True)),
+])
+def test_non_default_options_bit_exact(ref_lib, hostsim_lib, name, extra):
+    kw = dict(distribution_mode="hard", num_levels=200, start_level=0, rand_seed=0)
+    kw.update(extra)
+    ref, dut = make_pair(hostsim_lib, 8, name, **kw)
+    run_lockstep(ref, dut, 250)
+    ref.close()
+    dut.close()
+
+
+@pytest.mark.parametrize("name", ALL_GAMES.split(","))
+def test_state_blobs_byte_identical_and_portable(ref_lib, hostsim_lib, name):
+    from oracle.ref_env import RefVecEnv, default_pack
+
+    kw = dict(distribution_mode="hard", num_levels=200, start_level=0)
+    run_state_roundtrip(lambda seed: RefVecEnv(4, name, rand_seed=seed, **kw),
+                        lambda seed: RefVecEnv(4, name, rand_seed=seed, lib_path=hostsim_lib, resource_root=default_pack(), **kw),
+                        4, 100)
 
 
 def test_unrestricted_levels_and_other_seed(ref_lib, hostsim_lib):

@@ -45,6 +45,51 @@ def test_libenv_host_buffers_bit_exact(ref_lib, product_lib, name, mode, n, step
     dut.close()
 
 
+@pytest.mark.parametrize("name", ["coinrun", "bossfight", "chaser", "starpilot", "jumper", "plunder", "heist", "leaper"])
+def test_state_blobs_byte_identical_and_portable(ref_lib, product_lib, name):
+    from helpers import run_state_roundtrip
+    from oracle.ref_env import RefVecEnv, default_pack
+
+    kw = dict(distribution_mode="hard", num_levels=200, start_level=0)
+    run_state_roundtrip(lambda seed: RefVecEnv(8, name, rand_seed=seed, **kw),
+                        lambda seed: RefVecEnv(8, name, rand_seed=seed, lib_path=product_lib, resource_root=default_pack(), **kw),
+                        8, 150)
+
+
+def test_python_api_state_roundtrip(product_lib):
+    """ProcgenGym3Env.get_state / set_state (env.py:140-153): restoring a snapshot replays the same frames."""
+    import torch
+
+    from procgen_b200 import ProcgenGym3Env
+
+    env = ProcgenGym3Env(16, "coinrun", distribution_mode="hard", num_levels=0, start_level=0, rand_seed=7)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    acts = torch.randint(0, 15, (40, 16), device="cuda", dtype=torch.int32, generator=gen)
+    for t in range(10):
+        env.act(acts[t])
+        env.observe()
+    states = env.callmethod("get_state")
+    frames = []
+    for t in range(10, 40):
+        env.act(acts[t])
+        frames.append(env.observe()[1]["rgb"].clone())
+    env.callmethod("set_state", states)
+    for t in range(10, 40):
+        env.act(acts[t])
+        assert torch.equal(env.observe()[1]["rgb"], frames[t - 10])
+    assert env.errors() == 0
+    env.close()
+
+
+def test_sixteen_game_list_bit_exact(ref_lib, product_lib):
+    """BASELINE.json configs[4] shape on one GPU: env n plays game n % 16."""
+    names = "bigfish,bossfight,caveflyer,chaser,climber,coinrun,dodgeball,fruitbot,heist,jumper,leaper,maze,miner,ninja,plunder,starpilot"
+    ref, dut = make_pair(product_lib, 64, names, distribution_mode="hard", num_levels=200, start_level=0, rand_seed=0)
+    run_lockstep(ref, dut, 500)
+    ref.close()
+    dut.close()
+
+
 @pytest.mark.parametrize("fixture", sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz")))
 def test_device_api_reproduces_golden(product_lib, fixture):
     import torch

@@ -32,6 +32,19 @@ def test_initial_level_seeds(ref_lib, asset_pack):
     ("bigfish", "hard", 64, 1000, (128.0, 525, 0)),
     ("maze", "hard", 64, 1000, (600.0, 143, 60)),
     ("heist", "hard", 64, 1000, (120.0, 66, 12)),
+    # the other twelve games, N=32, T=1500 (SURVEY §8c "further KATs")
+    ("bossfight", "hard", 32, 1500, (50.0, 1117, 4)),
+    ("caveflyer", "hard", 32, 1500, (100.0, 113, 10)),
+    ("chaser", "hard", 32, 1500, (286.96, 442, 0)),
+    ("climber", "hard", 32, 1500, (131.0, 91, 10)),
+    ("dodgeball", "hard", 32, 1500, (284.0, 435, 0)),
+    ("fruitbot", "hard", 32, 1500, (-752.0, 1280, 0)),
+    ("jumper", "hard", 32, 1500, (140.0, 97, 14)),
+    ("leaper", "hard", 32, 1500, (280.0, 297, 28)),
+    ("miner", "hard", 32, 1500, (164.0, 137, 0)),
+    ("ninja", "hard", 32, 1500, (220.0, 187, 22)),
+    ("plunder", "hard", 32, 1500, (334.0, 115, 0)),
+    ("starpilot", "hard", 32, 1500, (505.0, 568, 0)),
 ])
 def test_aggregate_known_answers(ref_lib, asset_pack, name, mode, n, steps, expect):
     """(sum reward, episode starts, level completes) under the §8c action recipe."""
@@ -46,7 +59,7 @@ def test_aggregate_known_answers(ref_lib, asset_pack, name, mode, n, steps, expe
         starts += int(first.sum())
         comp += int(env.info["prev_level_complete"].sum())
     env.close()
-    assert (tot, starts, comp) == expect
+    assert (round(tot, 2), starts, comp) == expect
 
 
 @pytest.mark.parametrize("fixture", sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz")) if os.path.isdir(GOLDEN) else [])
