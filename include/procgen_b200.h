@@ -193,6 +193,10 @@ LIBENV_API int64_t pgb200_kernel_launches(libenv_env *handle);
  * out[2] = number of launch pairs timed, out[3] = env-steps those launches processed; returns the
  * number of pairs. At most max_launch_pairs pairs are timed (further launches run untimed). */
 LIBENV_API int pgb200_kernel_timing_begin(libenv_env *handle, int max_launch_pairs);
+/* Measurement knob: chunks > 0 forces that many env chunks per game and step (0 = the default
+ * policy); serialize != 0 keeps every launch on the handle's stream, back to back, so a kernel's
+ * event-timed duration is its own and not shared with kernels of other chunks. */
+LIBENV_API void pgb200_set_launch_shape(libenv_env *handle, int chunks, int serialize);
 LIBENV_API int pgb200_kernel_timing_end(libenv_env *handle, double *out);
 
 /* 1 if this library was built for the GPU (the product), 0 for the CPU debug harness in tests/. */

@@ -396,6 +396,8 @@ struct VecEnv {
     bool timing = false;
 #endif
     static constexpr int kChunks = PG_STEP_CHUNKS;
+    int force_chunks = 0;            // measurement knobs (pgb200_set_launch_shape)
+    bool serialize_launches = false;
     static constexpr int kMaxTickets = 64;
     unsigned int *d_tickets = nullptr;
     int max_logic_blocks = 1 << 30;
@@ -435,11 +437,13 @@ struct VecEnv {
     void launch(bool init) {
         const int G = (int)games.size();
         const int per_game = num_envs / G;
-        int chunks = kChunks;
-        if (per_game < 4096 * chunks)
+        int chunks = force_chunks > 0 ? force_chunks : kChunks;
+        if (force_chunks <= 0 && per_game < 4096 * chunks)
             chunks = 1;
 #ifndef PG_HOSTSIM
-        const int nstreams = chunks > 1 ? kAuxStreams : 0;
+        // more than one (logic, render) pair in the step — env chunks of one game, or the games of a
+        // joint list — are spread over the auxiliary streams so they overlap on the SMs
+        const int nstreams = (chunks * G > 1 && !serialize_launches) ? kAuxStreams : 0;
         if (nstreams) {
             CUDA_CHECK(cudaEventRecord(ev_fork, stream));
             for (int s = 0; s < nstreams; s++) CUDA_CHECK(cudaStreamWaitEvent(aux[s], ev_fork, 0));
@@ -1154,6 +1158,14 @@ void set_state(libenv_env *handle, int env_idx, char *data, int length) {
 }
 
 int64_t pgb200_kernel_launches(libenv_env *handle) { return ((VecEnv *)handle)->launches; }
+
+void pgb200_set_launch_shape(libenv_env *handle, int chunks, int serialize) {
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+    v->force_chunks = chunks;
+    v->serialize_launches = serialize != 0;
+}
 
 int pgb200_kernel_timing_begin(libenv_env *handle, int max_launch_pairs) {
 #ifndef PG_HOSTSIM

@@ -292,6 +292,10 @@ class BaseProcgenEnv:
     def kernel_launches(self) -> int:
         return int(self._lib.pgb200_kernel_launches(self._h))
 
+    def set_launch_shape(self, chunks: int = 0, serialize: bool = False) -> None:
+        """Measurement knob (see pgb200_set_launch_shape): env chunks per step, launches back to back."""
+        self._lib.pgb200_set_launch_shape(self._h, int(chunks), int(bool(serialize)))
+
     def kernel_timing_begin(self, max_launch_pairs: int) -> None:
         """Bracket every (logic, render) kernel pair with CUDA events until kernel_timing_end()."""
         self._lib.pgb200_kernel_timing_begin(self._h, int(max_launch_pairs))
@@ -311,7 +315,9 @@ class BaseProcgenEnv:
         torch = self._torch
         world = dist.get_world_size()
         if dist.get_rank() == dst:
-            out = torch.empty((world * self.num, 64, 64, 3), dtype=torch.uint8, device=self._dev)
+            out = getattr(self, "_gather_buf", None)
+            if out is None or out.shape[0] != world * self.num:
+                out = self._gather_buf = torch.empty((world * self.num, 64, 64, 3), dtype=torch.uint8, device=self._dev)
             dist.gather(self._rgb, list(out.chunk(world, dim=0)), dst=dst)
             return out
         dist.gather(self._rgb, None, dst=dst)

@@ -47,7 +47,7 @@ class DeviceBuffers(C.Structure):
 EXPORTS = ["libenv_version", "libenv_make", "libenv_get_tensortypes", "libenv_set_buffers", "libenv_observe",
            "libenv_act", "libenv_close", "pgb200_get_device_buffers", "pgb200_set_stream", "pgb200_act_device",
            "pgb200_sync", "pgb200_get_errors", "pgb200_debug_cycles", "pgb200_debug_read_env", "pgb200_kernel_launches", "pgb200_is_device_build",
-           "pgb200_kernel_timing_begin", "pgb200_kernel_timing_end", "get_state", "set_state"]
+           "pgb200_kernel_timing_begin", "pgb200_kernel_timing_end", "get_state", "set_state", "pgb200_set_launch_shape"]
 
 _lib = None
 
@@ -79,6 +79,8 @@ def bind(lib):
     lib.get_state.restype = C.c_int
     lib.set_state.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     lib.set_state.restype = None
+    lib.pgb200_set_launch_shape.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.pgb200_set_launch_shape.restype = None
     lib.pgb200_kernel_timing_begin.argtypes = [C.c_void_p, C.c_int]
     lib.pgb200_kernel_timing_begin.restype = C.c_int
     lib.pgb200_kernel_timing_end.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
