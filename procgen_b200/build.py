@@ -30,6 +30,15 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
+def build_variant(name, extra_flags):
+    """A tuning variant of the product library (same sources, extra -D flags) next to it; selected at
+    run time with PROCGEN_B200_LIB. Used by tools/ for A/B kernel experiments only."""
+    out = os.path.join(PKG_DIR, f"libprocgen_b200_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc, *NVCC_FLAGS, *extra_flags, os.path.join(CSRC, "pg_runtime.cu"), "-o", out, "-lz", "-ldl"])
+    return out
+
+
 def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH

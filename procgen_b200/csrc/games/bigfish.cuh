@@ -18,6 +18,7 @@ struct BigFish : Defaults<BigFish>, DrawDefaults<BigFish> {
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "bigfish";
+    static constexpr bool DRAWS_GRID = false;  // entities only; the grid stays all SPACE
 
     // bigfish.cpp:8-16
     static constexpr int COMPLETION_BONUS = 10;

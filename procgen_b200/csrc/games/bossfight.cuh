@@ -23,6 +23,7 @@ struct BossfightGame : Defaults<BossfightGame>, DrawDefaults<BossfightGame> {
     static constexpr int MAX_ROT_BLITS = 352;  // every enemy bullet and its trails spin (vrot = PI/8)
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "bossfight";
+    static constexpr bool DRAWS_GRID = false;  // entities only; the grid stays all SPACE
 
     // bossfight.cpp:8-30
     static constexpr int COMPLETION_BONUS = 10, POSITIVE_REWARD = 1;
@@ -35,6 +36,7 @@ struct BossfightGame : Defaults<BossfightGame>, DrawDefaults<BossfightGame> {
     static PG_HD Entity &boss(Ctx &c) { return c.ents[st(c).boss_idx]; }
     static PG_HD Entity &shields(Ctx &c) { return c.ents[st(c).shields_idx]; }
 
+    static constexpr bool HAS_ENTITY_HOOKS = true;
     static PG_HD void on_entity_moved(Ctx &c, int from, int to) {
         BossfightState &s = st(c);
         if (s.boss_idx == from)

@@ -34,6 +34,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
     static PG_HD bool is_wall(int obj) { return obj == CAVEWALL || obj == CAVEWALL_TOP; }
     static PG_HD bool can_support(Ctx &c, int obj) { return is_wall(obj) || obj == c.h->out_of_bounds_object; }
 
+    static constexpr bool HAS_ENTITY_HOOKS = true;
     static PG_HD void on_entity_moved(Ctx &c, int from, int to) {
         if (st(c).goal_idx == from)
             st(c).goal_idx = to;

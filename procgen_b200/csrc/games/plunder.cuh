@@ -23,6 +23,7 @@ struct PlunderGame : Defaults<PlunderGame>, DrawDefaults<PlunderGame> {
     static constexpr int MAX_ROT_BLITS = 4;
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "plunder";
+    static constexpr bool DRAWS_GRID = false;  // entities only; the grid stays all SPACE
 
     // plunder.cpp:8-15
     static constexpr float COMPLETION_BONUS = 10.0f;

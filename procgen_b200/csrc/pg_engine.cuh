@@ -501,13 +501,23 @@ struct Engine {
         obj.vy *= vy_pct;
     }
 
-    // basic-abstract-game.cpp:1086-1098 (`given` is always the live list; the count is latched)
+    // basic-abstract-game.cpp:1086-1098 (`given` is always the live list; the count is latched).
+    // The reference walks the list from the back: smart_step entities run the sub-step physics
+    // (which reads every other entity), all others just integrate their own fields. Entities that
+    // only integrate commute with each other, so each run of them between two smart entities is
+    // stepped by the warp's lanes in parallel; smart entities keep their place in the order.
     static PG_HD void step_entities(Ctx &c) {
-        int entities_count = c.h->n_ents;
-        for (int i = entities_count - 1; i >= 0; i--) {
-            if (c.ents[i].smart_step)
-                basic_step_object(c, i);
-            entity_step(c.ents[i]);
+        int hi = c.h->n_ents;
+        while (hi > 0) {
+            Entity *ents = c.ents;
+            const int s = pg_scan_down(hi, [=](int k) { return ents[k].smart_step != 0; });
+            const int lo = s + 1;  // entities [lo, hi) only integrate
+            pg_warp_for(hi - lo, [=](int k) { entity_step(ents[lo + k]); });
+            if (s < 0)
+                break;
+            basic_step_object(c, s);
+            entity_step(c.ents[s]);
+            hi = s;
         }
     }
 
@@ -530,11 +540,71 @@ struct Engine {
 
     // basic-abstract-game.cpp:748-756. Order-preserving compaction; an erased agent moves to the
     // ghost slot so later reads through `agent` still work (the reference keeps it alive via
-    // shared_ptr).
+    // shared_ptr). On the device each lane owns one entity of a 32-entity chunk: the erase tests
+    // run in parallel, a ballot + popcount gives every survivor its destination, all lanes read
+    // their record before any lane writes (destinations never lie beyond the chunk's sources),
+    // and the per-game bookkeeping hooks then run in list order, warp-uniformly.
     static PG_HD void erase_if_needed(Ctx &c) {
         const int n = c.h->n_ents;
         int w = 0;
         int agent_idx = c.h->agent_idx;
+#if defined(__CUDA_ARCH__)
+        const int lane = (int)(threadIdx.x & 31u);
+        const int old_agent = c.h->agent_idx;
+        // common case first: nothing to erase
+        {
+            Ctx *cp = &c;
+            ScanUpIter it(0, n);
+            const int first = it.next([=](int k) {
+                const Entity &e = cp->ents[k];
+                return e.will_erase || (e.auto_erase && is_out_of_bounds(*cp, e));
+            });
+            if (first < 0)
+                return;
+            w = first & ~31;  // whole chunks before the first erased entity stay where they are
+        }
+        for (int base = w; base < n; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < n;
+            Entity e;
+            bool erase = false;
+            if (valid) {
+                e = c.ents[i];
+                erase = e.will_erase || (e.auto_erase && is_out_of_bounds(c, e));
+            }
+            const unsigned keepmask = __ballot_sync(0xffffffffu, valid && !erase);
+            const unsigned erasemask = __ballot_sync(0xffffffffu, erase);
+            const int dest = w + __popc(keepmask & ((1u << lane) - 1u));
+            __syncwarp();
+            if (valid && !erase && dest != i)
+                c.ents[dest] = e;
+            if (valid && i == old_agent && erase)
+                c.ents[c.ent_cap] = e;
+            const unsigned agent_lane_mask = __ballot_sync(0xffffffffu, valid && i == old_agent);
+            if (agent_lane_mask) {
+                const int al = __ffs((int)agent_lane_mask) - 1;
+                const int adest = __shfl_sync(0xffffffffu, dest, al);
+                agent_idx = ((erasemask >> al) & 1u) ? c.ent_cap : adest;
+            }
+            __syncwarp();
+            if (G::HAS_ENTITY_HOOKS) {
+                unsigned touched = erasemask | keepmask;
+                while (touched) {
+                    const int l = __ffs((int)touched) - 1;
+                    touched &= touched - 1;
+                    const int src = base + l;
+                    if ((erasemask >> l) & 1u) {
+                        G::on_entity_erased(c, src);
+                    } else {
+                        const int d = __shfl_sync(0xffffffffu, dest, l);
+                        if (d != src)
+                            G::on_entity_moved(c, src, d);
+                    }
+                }
+            }
+            w += __popc(keepmask);
+        }
+#else
         for (int i = 0; i < n; i++) {
             Entity &e = c.ents[i];
             bool erase = e.will_erase || (e.auto_erase && is_out_of_bounds(c, e));
@@ -554,6 +624,7 @@ struct Engine {
             }
             w++;
         }
+#endif
         c.h->n_ents = w;
         c.h->agent_idx = agent_idx;
     }
@@ -812,11 +883,16 @@ struct Defaults {
     static PG_HD void update_agent_velocity(Ctx &c) { E::default_update_agent_velocity(c); }
     static PG_HD void game_step(Ctx &c) { E::basic_game_step(c); }
     static PG_HD void game_reset(Ctx &c) { E::basic_game_reset(c); }
-    // bookkeeping hooks for games that hold references to entities (shared_ptr members)
+    // bookkeeping hooks for games that hold references to entities (shared_ptr members); a game
+    // that defines them sets HAS_ENTITY_HOOKS
+    static constexpr bool HAS_ENTITY_HOOKS = false;
     static PG_HD void on_entity_moved(Ctx &c, int from, int to) {}
     static PG_HD void on_entity_erased(Ctx &c, int idx) {}
 
     // ---- draw-side hooks (basic-abstract-game.cpp:432-446, 799-817, 1048-1050)
+    // false = the game never writes its grid (all SPACE) and always draws the whole world
+    // (center_agent forced off): the frame then carries no cell blits at all
+    static constexpr bool DRAWS_GRID = true;
     static PG_HD int image_for_type(Ctx &c, int type) { return type < 0 ? -type : type; }
     static PG_HD int theme_for_grid_obj(Ctx &c, int type) { return 0; }
     static PG_HD bool should_draw_entity(Ctx &c, int ei) { return true; }

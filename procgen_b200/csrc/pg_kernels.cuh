@@ -168,8 +168,12 @@ template <class G, class Frame>
 __device__ __forceinline__ void env_render_pixels(const KParams &p, int env, const Frame &f, int tid, int nthreads) {
     uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3));
     const int j = tid & 3;
+    // nthreads is a multiple of RES_W: a thread's pixels all lie in one column
+    const int px = tid & (RES_W - 1);
+    typename Raster<G, Frame>::ColumnCtx cc;
+    Raster<G, Frame>::column_begin(f, px, cc);
     for (int pix = tid; pix < RES_W * RES_H; pix += nthreads) {
-        const uint32_t c = rgb24_of(Raster<G, Frame>::shade_pixel(f, pix & (RES_W - 1), pix >> 6, p.atlas));
+        const uint32_t c = rgb24_of(Raster<G, Frame>::shade_pixel(f, cc, px, pix >> 6, p.atlas));
         const uint32_t cn = __shfl_down_sync(0xffffffffu, c, 1);
         if (j != 3)
             out[(pix >> 2) * 3 + j] = (c >> (8 * j)) | (cn << (24 - 8 * j));
@@ -201,7 +205,7 @@ PG_HD void env_render_quad(const KParams &p, int env, const Frame &f, int quad) 
 // Frame sizing per game: visible window (cells per side) and entity capacity.
 template <class G>
 struct FrameFor {
-    using type = FrameT<G::MAX_VIEW_CELLS, G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
+    using type = FrameT<(G::DRAWS_GRID ? G::MAX_VIEW_CELLS : 1), G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
 };
 
 }  // namespace pg

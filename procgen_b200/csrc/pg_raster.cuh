@@ -15,7 +15,7 @@
 //   prepare_camera   logic thread  prepare_for_drawing -> env header (runs in the logic kernel)
 //   frame_begin      all threads   thread 0: window + background/overlay blits; threads i<nx / j<ny:
 //                                  geometry + pixel span of grid column i / row j
-//   frame_build      all threads   warp 0: entities -> blits, culled and compacted in draw order with
+//   frame_build      all threads   entities -> blits (one entity per thread and round), culled and compacted in draw order with
 //                                  warp ballots; other warps: one blit per visible grid cell and the
 //                                  pixel-column/row -> cell lookup tables (fp64 math happens here,
 //                                  once per sprite instead of once per pixel)
@@ -183,7 +183,7 @@ struct RotXform {
 };
 
 PG_HD void rot_span(RotBlit &rb, int x, int len, int y) {
-    if (y < 0 || y >= RES_H)
+    if (y < (rb.pad & 0xff) || y >= ((rb.pad >> 8) & 0xff))  // outside the cleared row window (and the device)
         return;
     if (x < 0) {
         len += x;
@@ -489,7 +489,7 @@ PG_HD void rot_transform_image(RotBlit &rb, int sw, int sh, const double *r, con
 
 // QRasterPaintEngine::drawImage under a rotating matrix: fills rb, returns false if nothing drawn
 PG_HD void rot_draw(RotBlit &rb, int sw, int sh, const double *r, const RotXform &m) {
-    for (int y = 0; y < RES_H; y++) rb.x1[y] = rb.x2[y] = 0;
+    rb.pad = 0;  // row window [lo, hi) the spans can fall in: lo | hi << 8 (set below)
     rb.absolute = 0;
     rb.dudx = rb.dvdx = rb.dudy = rb.dvdy = rb.u0 = rb.v0 = 0;
     rb.m11 = rb.m12 = rb.m21 = rb.m22 = rb.dx = rb.dy = 0;
@@ -503,6 +503,19 @@ PG_HD void rot_draw(RotBlit &rb, int sw, int sh, const double *r, const RotXform
         if (X > maxx) maxx = X;
         if (Y < miny) miny = Y;
         if (Y > maxy) maxy = Y;
+    }
+    {
+        // only the rows the quad can touch are cleared here and scanned by the caller afterwards
+        // (every rasteriser below emits spans inside the quad's bounding box, +-1 row of rounding)
+        int lo = (int)pg_dfloor(miny) - 2, hi = (int)pg_dceil(maxy) + 3;
+        if (lo < 0) lo = 0;
+        if (hi > RES_H) hi = RES_H;
+        if (!(maxy >= -2) || !(miny <= RES_H + 2) || hi <= lo) {
+            rb.pad = 0;
+            return;
+        }
+        for (int y = lo; y < hi; y++) rb.x1[y] = rb.x2[y] = 0;
+        rb.pad = lo | (hi << 8);
     }
     if (maxx - minx >= 16 && maxy - miny >= 16) {
         rot_transform_image(rb, sw, sh, r, m);
@@ -638,6 +651,7 @@ PG_HD RotBlit *span_blit_begin(Frame &f, Blit &b, int k, uint32_t argb_premultip
         return nullptr;
     RotBlit &rb = f.rot[slot];
     for (int y = 0; y < RES_H; y++) rb.x1[y] = rb.x2[y] = 0;
+    rb.pad = RES_H << 8;  // row window = the whole device
     b.ix = slot;
     b.src = argb_premultiplied;
     b.opacity = 256;
@@ -931,7 +945,8 @@ struct Raster {
         RotBlit &rb = f.rot[slot];
         rot_draw(rb, sd.w, sd.h, r, m);
         int y0 = RES_H, y1 = -1, x0 = RES_W, x1 = 0;
-        for (int y = 0; y < RES_H; y++) {
+        const int row_lo = rb.pad & 0xff, row_hi = (rb.pad >> 8) & 0xff;
+        for (int y = row_lo; y < row_hi; y++) {
             if (rb.x2[y] > rb.x1[y]) {
                 if (y < y0) y0 = y;
                 y1 = y;
@@ -1034,6 +1049,13 @@ struct Raster {
         const Camera cam = camera_of(h);
         int low_x, low_y, nx, ny;
         grid_window(h, low_x, low_y, nx, ny);
+        if (!G::DRAWS_GRID) {
+            // the game never puts anything into its grid and never looks outside it: no cell blits
+            if (h.options.center_agent)
+                h.err |= ERR_UNSUPPORTED;  // a centred view would show out-of-bounds cells
+            nx = 0;
+            ny = 0;
+        }
         bool overflow = false;
         if (nx > Frame::kMaxCells1D) { nx = Frame::kMaxCells1D; overflow = true; }
         if (ny > Frame::kMaxCells1D) { ny = Frame::kMaxCells1D; overflow = true; }
@@ -1053,6 +1075,14 @@ struct Raster {
                 h.err |= ERR_BLIT_OVERFLOW;
             if (h.options.use_backgrounds)
                 G::make_background_blits(c, f);
+            // the usual case — one opaque background image covering the whole device — lets the
+            // shader skip the box test and the blend (Frame::pad = 1)
+            f.pad = 0;
+            if (f.n_bg == 1) {
+                const Blit &b0 = f.bg[0];
+                if (b0.kind == BLIT_IMAGE && b0.x1 == 0 && b0.y1 == 0 && b0.w == RES_W && b0.h == RES_H && b0.opacity == 256 && !b0.mirror)
+                    f.pad = 1;
+            }
             if (h.has_useful_vel_info && h.options.paint_vel_info) {
                 // draw_foreground's last step (basic-abstract-game.cpp:960-969): two grey squares
                 // whose shade encodes the agent's velocity; to_shade is qt-utils.h:21-28
@@ -1190,17 +1220,50 @@ struct Raster {
         return 1;
     }
 
+    // Tile j of tiled entity ei (same geometry as the tiled branch of entity_blits)
+    static PG_HD void entity_tile_blit(Ctx &c, Frame &f, int ei, int j, Blit &b) {
+        const Entity &o = c.ents[ei];
+        double r[4];
+        object_rect(f.cam, o, r);
+        const float tile_ratio = G::get_tile_aspect_ratio(c, ei);
+        const int img_type = G::image_for_type(c, o.image_type);
+        double adj[4];
+        if (G::get_adjusted_image_rect(c, img_type, adj))
+            adjust_rect(r, adj);
+        const int nt = tile_count(r, tile_ratio);
+        double tr[4];
+        tile_rect(r, tile_ratio, nt, j, tr);
+        make_sprite_blit_noadjust(c, f, b, tr, o.is_reflected != 0, img_type, o.image_theme, o.alpha);
+    }
+
     // Entities -> blits in draw order (draw_entities z=-1 / 0 / 1, basic-abstract-game.cpp:1059-1066),
-    // culled. `lane`/`gsize`: the cooperating group (a full warp on the device, 1 in the host
-    // harness). Each lane owns one entity per round; a warp prefix sum of the per-entity blit counts
-    // keeps the list in draw order.
-    static PG_HD void build_entity_blits(Ctx &c, Frame &f, int lane, int gsize) {
+    // culled. The whole CTA cooperates (the host harness runs it with one thread): each thread owns
+    // one entity per round and builds its blit(s) — for a rotated sprite that is a scan conversion
+    // in fp64, the expensive part — and a block-wide prefix sum of the per-entity blit counts keeps
+    // the list in draw order.
+    static PG_HD void build_entity_blits(Ctx &c, Frame &f, int tid, int nthreads) {
         const int n = c.h->n_ents;
         int count = 0;
         int below = 0;
+#if defined(__CUDA_ARCH__)
+        __shared__ int warp_tot[32];
+        // tiled entities (walls drawn as up to ~45 repeats of one sprite): the owner thread only
+        // reserves the slots; the tiles themselves are built by all threads afterwards
+        constexpr int kMaxTileJobs = 64;
+        __shared__ int job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs];
+        __shared__ int n_jobs;
+        const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+        const bool multi_warp = nthreads > 32;
+        if (tid == 0)
+            n_jobs = 0;
+        if (multi_warp)
+            __syncthreads();
+        else
+            __syncwarp();
+#endif
         for (int z = -1; z <= 1; z++) {
-            for (int base = 0; base < n; base += gsize) {
-                const int ei = base + lane;
+            for (int base = 0; base < n; base += nthreads) {
+                const int ei = base + tid;
                 Blit single;
                 blit_clear(single);
                 int mine = 0;
@@ -1219,45 +1282,95 @@ struct Raster {
                     if (lane >= d)
                         incl += t;
                 }
-                pos = count + incl - mine;
-                total = __shfl_sync(0xffffffffu, incl, 31);
+                if (multi_warp) {
+                    if (lane == 31)
+                        warp_tot[warp] = incl;
+                    __syncthreads();
+                    int woff = 0;
+                    total = 0;
+                    for (int w = 0; w < nwarps; w++) {
+                        const int t = warp_tot[w];
+                        if (w < warp)
+                            woff += t;
+                        total += t;
+                    }
+                    pos = count + woff + incl - mine;
+                } else {
+                    pos = count + incl - mine;
+                    total = __shfl_sync(0xffffffffu, incl, 31);
+                }
 #endif
                 if (mine > 0) {
                     if (pos + mine <= Frame::kMaxEntBlits) {
                         if (!tiled) {
                             f.ents[pos] = single;
                         } else {
-                            Blit *dst = f.ents + pos;
-                            entity_blits(c, f, ei, true, single, [=](int j, const Blit &b) { dst[j] = b; });
+#if defined(__CUDA_ARCH__)
+                            const int job = mine > 1 ? atomicAdd(&n_jobs, 1) : kMaxTileJobs;
+                            if (job < kMaxTileJobs) {
+                                job_ei[job] = ei;
+                                job_pos[job] = pos;
+                                job_n[job] = mine;
+                            } else
+#endif
+                            {
+                                Blit *dst = f.ents + pos;
+                                entity_blits(c, f, ei, true, single, [=](int j, const Blit &b) { dst[j] = b; });
+                            }
                         }
                     } else {
                         c.h->err |= ERR_BLIT_OVERFLOW;
                     }
                 }
                 count += total;
+#if defined(__CUDA_ARCH__)
+                if (multi_warp)
+                    __syncthreads();  // warp_tot is reused by the next round
+#endif
             }
             if (z == -1)
                 below = count;
         }
+#if defined(__CUDA_ARCH__)
+        if (multi_warp)
+            __syncthreads();
+        else
+            __syncwarp();
+        {
+            const int nj = n_jobs < kMaxTileJobs ? n_jobs : kMaxTileJobs;
+            for (int job = 0; job < nj; job++) {
+                const int ei = job_ei[job], pos = job_pos[job], nt = job_n[job];
+                for (int j = tid; j < nt; j += nthreads) entity_tile_blit(c, f, ei, j, f.ents[pos + j]);
+            }
+        }
+#endif
         if (count > Frame::kMaxEntBlits)
             count = Frame::kMaxEntBlits;
         if (below > count)
             below = count;
-        if (lane == 0) {
+        if (tid == 0) {
             f.n_ent = count;
             f.n_ent_below = below;
         }
     }
 
-    // ---- phase C. Threads [0, ent_group) build the entity list; the rest build cells + lookups.
-    static PG_HD void frame_build(Ctx &c, Frame &f, int tid, int nthreads, int ent_group) {
-        if (tid < ent_group) {
-            build_entity_blits(c, f, tid, ent_group);
-            if (nthreads > ent_group)
+    // ---- phase C. Few entities: warp 0 builds the entity list while the other warps build the
+    // cells and the pixel -> cell lookups. Many entities (bullet-heavy frames, tiled walls): the
+    // whole CTA builds the list, then the cells.
+    static PG_HD void frame_build(Ctx &c, Frame &f, int tid, int nthreads, int /*unused*/) {
+        int wtid = tid, wn = nthreads;
+        if (nthreads > 32 && c.h->n_ents <= 32) {
+            if (tid < 32) {
+                build_entity_blits(c, f, tid, 32);
                 return;
+            }
+            wtid = tid - 32;
+            wn = nthreads - 32;
+        } else {
+            build_entity_blits(c, f, tid, nthreads);
         }
-        const int wtid = (nthreads > ent_group) ? tid - ent_group : tid;
-        const int wn = (nthreads > ent_group) ? nthreads - ent_group : nthreads;
+        if (!G::DRAWS_GRID)
+            return;
         for (int px = wtid; px < RES_W + RES_H; px += wn) {
             if (px < RES_W)
                 cell_lookup(f.col_p1, f.col_p2, f.nx, px, f.col_lo[px], f.col_hi[px]);
@@ -1314,31 +1427,65 @@ struct Raster {
     }
 
     // ---- phase D: the gather. Returns 0xFFRRGGBB (Format_RGB32).
-    static PG_HD uint32_t shade_pixel(const Frame &f, int px, int py, const uint32_t *atlas) {
+    // A thread shades one pixel column (px fixed, py varies), so everything that depends on the
+    // column only is loaded once into a ColumnCtx and reused for all its rows.
+    struct ColumnCtx {
+        uint64_t colmask[Frame::kEntWords];
+        int nw;          // 64-blit mask words in use this frame: (n_ent + 63) / 64
+        int clo, chi;    // grid columns covering this pixel column (255 = none)
+        uint32_t bg_sx;  // full-screen background: source column of this pixel column
+        bool bg_full;
+    };
+    static PG_HD void column_begin(const Frame &f, int px, ColumnCtx &cc) {
+        cc.nw = (f.n_ent + 63) >> 6;
+#pragma unroll
+        for (int w = 0; w < Frame::kEntWords; w++) cc.colmask[w] = w < cc.nw ? f.ent_colmask[px][w] : 0;
+        cc.clo = 255;
+        cc.chi = 0;
+        if (G::DRAWS_GRID) {
+            cc.clo = f.col_lo[px];
+            cc.chi = f.col_hi[px];
+        }
+        cc.bg_full = f.pad == 1;
+        cc.bg_sx = cc.bg_full ? (f.bg[0].basex + (uint32_t)f.bg[0].ix * (uint32_t)px) >> 16 : 0;
+    }
+    static PG_HD uint32_t shade_pixel(const Frame &f, const ColumnCtx &cc, int px, int py, const uint32_t *atlas) {
         uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
-        for (int i = 0; i < f.n_bg; i++) dst = apply_blit(f.bg[i], px, py, dst, atlas, f.rot);
+        if (cc.bg_full) {
+            const Blit &b = f.bg[0];
+            const uint32_t sy = (b.srcy + (uint32_t)b.iy * (uint32_t)py) >> 16;
+            dst = atlas[b.src + sy * b.sw + cc.bg_sx];  // RGB32 background: alpha 255, replaces dst
+        } else {
+            for (int i = 0; i < f.n_bg; i++) dst = apply_blit(f.bg[i], px, py, dst, atlas, f.rot);
+        }
         uint64_t above[Frame::kEntWords];
         const int nb = f.n_ent_below;
+#pragma unroll
         for (int w = 0; w < Frame::kEntWords; w++) {
-            uint64_t m = f.ent_rowmask[py][w] & f.ent_colmask[px][w];
-            // entities with render_z == -1 go under the grid
-            const int lo = nb - w * 64;
-            const uint64_t below_bits = lo <= 0 ? 0 : (lo >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << lo) - 1));
-            uint64_t mb = m & below_bits;
-            above[w] = m & ~below_bits;
-            while (mb) {
-                const int i = ctz64(mb);
-                mb &= mb - 1;
-                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
+            above[w] = 0;
+            if (w < cc.nw) {
+                uint64_t m = f.ent_rowmask[py][w] & cc.colmask[w];
+                // entities with render_z == -1 go under the grid
+                const int lo = nb - w * 64;
+                const uint64_t below_bits = lo <= 0 ? 0 : (lo >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << lo) - 1));
+                uint64_t mb = m & below_bits;
+                above[w] = m & ~below_bits;
+                while (mb) {
+                    const int i = ctz64(mb);
+                    mb &= mb - 1;
+                    dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
+                }
             }
         }
-        const int clo = f.col_lo[px], chi = f.col_hi[px];
-        const int rlo = f.row_lo[py], rhi = f.row_hi[py];
-        if (clo != 255 && rlo != 255) {
-            for (int ci = clo; ci <= chi; ci++)
-                for (int cj = rlo; cj <= rhi; cj++)
-                    dst = apply_blit(f.cells[ci * f.ny + cj], px, py, dst, atlas, f.rot);
+        if (G::DRAWS_GRID) {
+            const int rlo = f.row_lo[py], rhi = f.row_hi[py];
+            if (cc.clo != 255 && rlo != 255) {
+                for (int ci = cc.clo; ci <= cc.chi; ci++)
+                    for (int cj = rlo; cj <= rhi; cj++)
+                        dst = apply_blit(f.cells[ci * f.ny + cj], px, py, dst, atlas, f.rot);
+            }
         }
+#pragma unroll
         for (int w = 0; w < Frame::kEntWords; w++) {
             uint64_t ma = above[w];
             while (ma) {
@@ -1349,6 +1496,11 @@ struct Raster {
         }
         for (int i = 0; i < f.n_overlay; i++) dst = apply_blit(f.overlay[i], px, py, dst, atlas, f.rot);
         return dst;
+    }
+    static PG_HD uint32_t shade_pixel(const Frame &f, int px, int py, const uint32_t *atlas) {
+        ColumnCtx cc;
+        column_begin(f, px, cc);
+        return shade_pixel(f, cc, px, py, atlas);
     }
 };
 

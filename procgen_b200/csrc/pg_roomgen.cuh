@@ -57,8 +57,11 @@ struct RoomGen {
         int16_t *g = c->grid;
         pg_warp_for(n, [=](int i) { g[i] = (int16_t)nc[i]; });
     }
-    // roomgen.cpp:38-69: flood from idx; members recorded in `room`, returns the member count
-    PG_HD int build_room(int idx) {
+    // roomgen.cpp:38-69: flood from idx; members get `stamp` in `room`, returns the member count.
+    // Rooms are connected components, hence disjoint: a cell carrying an older stamp can never be
+    // reached from a seed outside its room, so "not yet in THIS room" is room[cell] != stamp and the
+    // array needs no clearing between rooms.
+    PG_HD int build_room(int idx, int stamp) {
         Ctx &ctx = *c;
         if (E::get_obj_idx(ctx, idx) != SPACE)
             return 0;
@@ -76,10 +79,10 @@ struct RoomGen {
                         int next_idx = E::to_grid_idx(ctx, x + i, y + j);
                         if (next_idx < 0)
                             continue;  // INVALID_IDX: get_obj gives the out-of-bounds object, never SPACE here
-                        if (!room[next_idx] && E::get_obj_idx(ctx, next_idx) == SPACE) {
+                        if (room[next_idx] != stamp && E::get_obj_idx(ctx, next_idx) == SPACE) {
                             if (tail < 4 * n)
                                 queue[tail++] = next_idx;
-                            room[next_idx] = 1;
+                            room[next_idx] = stamp;
                             count++;
                         }
                     }
@@ -88,26 +91,31 @@ struct RoomGen {
         }
         return count;
     }
-    // roomgen.cpp:126-145: result flags in `best` (caller buffer [n]); returns its size
+    // roomgen.cpp:126-145: result flags in `best` (caller buffer [n]); returns its size. The
+    // reference builds a std::set per room and unions them into all_rooms; here every room stamps
+    // its cells with its ordinal, "already in some room" is a non-zero stamp, and the winner (first
+    // room of the largest size, as in the reference's strict `>`) is materialised once at the end.
     PG_HD int find_best_room(int32_t *best) {
         Ctx &ctx = *c;
-        int32_t *ar = all_rooms, *rm = room;
-        pg_warp_for(n, [=](int i) {
-            ar[i] = 0;
-            best[i] = 0;
-        });
+        int32_t *rm = room;
+        pg_warp_for(n, [=](int i) { rm[i] = 0; });
         int best_room_size = -1;
+        int best_stamp = 0;
+        int stamp = 0;
         for (int i = 0; i < n; i++) {
-            if (E::get_obj_idx(ctx, i) == SPACE && !all_rooms[i]) {
-                pg_warp_for(n, [=](int k) { rm[k] = 0; });
-                int sz = build_room(i);
-                pg_warp_for(n, [=](int k) { ar[k] |= rm[k]; });
+            if (E::get_obj_idx(ctx, i) == SPACE && !room[i]) {
+                stamp++;
+                int sz = build_room(i, stamp);
                 if (sz > best_room_size) {
                     best_room_size = sz;
-                    pg_warp_for(n, [=](int k) { best[k] = rm[k]; });
+                    best_stamp = stamp;
                 }
             }
         }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        pg_warp_for(n, [=](int k) { best[k] = (best_stamp != 0 && rm[k] == best_stamp) ? 1 : 0; });
         return best_room_size < 0 ? 0 : best_room_size;
     }
     // roomgen.cpp:71-124: BFS path src -> dst written to `path` (caller buffer), returns its length

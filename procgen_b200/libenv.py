@@ -94,7 +94,8 @@ def load(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    # PROCGEN_B200_LIB: another build of the same CUDA library (kernel tuning experiments, tools/)
+    p = path or os.environ.get("PROCGEN_B200_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(
             f"procgen_b200: CUDA library {p} is missing. Build it with "
