@@ -10,7 +10,7 @@ struct CaveFlyerGame : Defaults<CaveFlyerGame>, DrawDefaults<CaveFlyerGame> {
     static constexpr int ENT_CAP = 192;
     static constexpr int GRID_CAP = 60 * 60;
     static constexpr int SCRATCH_WORDS = 18 * GRID_CAP;
-    static constexpr int MAX_VISIBLE_ENTS = 128;
+    static constexpr int MAX_VISIBLE_ENTS = 64;
     static constexpr int MAX_ROT_BLITS = 32;
     static constexpr int MAX_VIEW_CELLS = 20;  // visibility 16 centred
     static constexpr const char *NAME = "caveflyer";
@@ -108,7 +108,13 @@ struct CaveFlyerGame : Defaults<CaveFlyerGame>, DrawDefaults<CaveFlyerGame> {
         h.out_of_bounds_object = WALL_OBJ;
         ctx_refresh(c);
         const int n = h.grid_size;
-        for (int i = 0; i < n; i++) c.grid[i] = (int16_t)(rand_rand01(rg) < .5 ? WALL_OBJ : SPACE);
+        {
+            // one rand01() per cell, in cell order (caveflyer.cpp:154-160): drawn in bulk, then thresholded
+            uint32_t *raw = reinterpret_cast<uint32_t *>(c.scratch);
+            rand_fill_raw(rg, raw, n);
+            int16_t *g0 = c.grid;
+            pg_warp_for(n, [=](int i) { g0[i] = (int16_t)((float)((double)raw[i] / 4294967296.0) < .5 ? WALL_OBJ : SPACE); });
+        }
         RoomGen<CaveFlyerGame> rm;
         rm.init(c, c.scratch, 12 * GRID_CAP);
         int32_t *best_room = c.scratch + 12 * GRID_CAP;

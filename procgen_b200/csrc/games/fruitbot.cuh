@@ -14,7 +14,7 @@ struct FruitBotGame : Defaults<FruitBotGame>, DrawDefaults<FruitBotGame> {
     static constexpr int ENT_CAP = 160;
     static constexpr int GRID_CAP = 20 * 60;
     static constexpr int SCRATCH_WORDS = 0;
-    static constexpr int MAX_VISIBLE_ENTS = 448;  // barriers are tiled: up to ~33 tiles per wall segment
+    static constexpr int MAX_VISIBLE_ENTS = 256;  // barriers are tiled; on-screen tiles only (measured peak 156)
     static constexpr int MAX_ROT_BLITS = 2;
     static constexpr int MAX_VIEW_CELLS = 24;
     static constexpr const char *NAME = "fruitbot";

@@ -170,7 +170,10 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         }
         if (h.options.distribution_mode == MemoryMode)
             h.timeout = 2000;
+        PG_PHASE_RESET(c);
+        PG_PHASE_BEGIN(c);
         E::basic_game_reset(c);
+        PG_PHASE_END(c, 0);
         h.out_of_bounds_object = WALL_OBJ;
         ctx_refresh(c);
         s.wall_theme = rand_randn(rg, NUM_WALL_THEMES);
@@ -187,15 +190,23 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
             MazeGen mg;
             mg.init(c, maze_dim);
             mg.generate_maze_no_dead_ends();
-            for (int i = 0; i < n; i++) {
-                int obj = mg.grid_get((i % w) / MAZE_SCALE + 1, (i / w) / MAZE_SCALE + 1);
+            PG_PHASE_END(c, 1);
+            // one rand01() per cell, in cell order (jumper.cpp:246-255): drawn in bulk behind the
+            // maze workspace, then thresholded against the maze cell's probability
+            uint32_t *raw = reinterpret_cast<uint32_t *>(c.scratch + MAZE_WORDS);
+            rand_fill_raw(rg, raw, n);
+            int16_t *g0 = c.grid;
+            const MazeGen *mgp = &mg;
+            pg_warp_for(n, [=](int i) {
+                int obj = mgp->grid_get((i % w) / MAZE_SCALE + 1, (i / w) / MAZE_SCALE + 1);
                 float prob = obj == WALL_OBJ ? .8 : .2;
-                c.grid[i] = (int16_t)(rand_rand01(rg) < prob ? WALL_OBJ : SPACE);
-            }
+                g0[i] = (int16_t)((float)((double)raw[i] / 4294967296.0) < prob ? WALL_OBJ : SPACE);
+            });
         }
 #if defined(__CUDA_ARCH__)
         __syncwarp();
 #endif
+        PG_PHASE_END(c, 2);
         RoomGen<JumperGame> rm;
         rm.init(c, c.scratch + MAZE_WORDS, ROOM_WORDS);
         int32_t *best_room = c.scratch + MAZE_WORDS + ROOM_WORDS;
@@ -206,6 +217,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         if (!rm.ok)
             return;
         for (int iteration = 0; iteration < 2; iteration++) rm.update();
+        PG_PHASE_END(c, 3);
         // border cells (jumper.cpp:258-267)
         for (int i = 0; i < w; i++) {
             E::set_obj(c, i, 0, CAVEWALL);
@@ -219,6 +231,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         __syncwarp();
 #endif
         int best_size = rm.find_best_room(best_room);
+        PG_PHASE_END(c, 4);
         if (best_size <= 0) {
             h.err |= ERR_FASSERT;
             return;
@@ -242,7 +255,9 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
             return;
         }
         int agent_cell = candidates[rand_randn(rg, ncand)];
+        PG_PHASE_END(c, 5);
         int path_len = rm.find_path(agent_cell, goal_cell, goal_path);
+        PG_PHASE_END(c, 6);
         bool should_prune = h.options.distribution_mode != MemoryMode;
         if (should_prune) {
             pg_warp_for(n, [=](int i) { wide_path[i] = 0; });
@@ -253,6 +268,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
             rm.expand_room(wide_path, 4);
             pg_warp_for(n, [=](int i) { g[i] = (int16_t)(wide_path[i] ? SPACE : CAVEWALL); });
         }
+        PG_PHASE_END(c, 7);
         s.goal_idx = E::spawn_entity_at_idx(c, goal_cell, .5, GOAL);
         float spike_prob = h.options.distribution_mode == MemoryMode ? 0 : .2;
         for (int i = 0; i < n; i++) {
@@ -295,6 +311,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         agent_of(c).ry = 0.4f;
         h.out_of_bounds_object = CAVEWALL;
         ctx_refresh(c);
+        PG_PHASE_END(c, 8);
     }
     // jumper.cpp:378-423
     static PG_HD void set_action_xy(Ctx &c, int move_action) {

@@ -19,7 +19,7 @@ struct LeaperGame : Defaults<LeaperGame>, DrawDefaults<LeaperGame> {
     static constexpr int ENT_CAP = 160;
     static constexpr int GRID_CAP = 20 * 20;
     static constexpr int SCRATCH_WORDS = 0;
-    static constexpr int MAX_VISIBLE_ENTS = 192;
+    static constexpr int MAX_VISIBLE_ENTS = 128;
     static constexpr int MAX_ROT_BLITS = 4;
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "leaper";
@@ -154,9 +154,17 @@ struct LeaperGame : Defaults<LeaperGame>, DrawDefaults<LeaperGame> {
         }
         s.goal_y = s.bottom_water_y + num_water_lanes + 1;
         const float lim = h.main_width / (min_car_speed < min_log_speed ? min_car_speed : min_log_speed);
-        for (int i = 0; (float)i < lim; i++) {
-            spawn_entities(c);
-            E::step_entities(c);
+        PG_PHASE_RESET(c);
+        {
+            PG_PHASE_BEGIN(c);
+            for (int i = 0; (float)i < lim; i++) {
+                spawn_entities(c);
+                PG_PHASE_END(c, 0);
+                E::step_entities(c);
+                PG_PHASE_END(c, 1);
+            }
+            PG_PHASE_NOTE(c, 2, lim);
+            PG_PHASE_NOTE(c, 3, c.h->n_ents);
         }
         E::add_entity_rxy(c, (float)(h.main_width / 2.0), (float)(s.goal_y - .5), 0, 0, (float)(h.main_width / 2.0), .5, FINISH_LINE);
     }
@@ -209,11 +217,14 @@ struct LeaperGame : Defaults<LeaperGame>, DrawDefaults<LeaperGame> {
         float log_vx = 0.0;
         Entity &a = agent_of(c);
         float margin = -1 * a.rx;
-        for (int i = 0; i < h.n_ents; i++) {
-            const Entity &m = c.ents[i];
-            if (m.type == LOG && E::has_collision(a, m, margin)) {
+        {
+            // the reference's ascending loop leaves the LAST overlapping log in log_vx: find it warp-wide
+            const Entity *ents = c.ents;
+            const Entity av = a;
+            const int li = pg_scan_down(h.n_ents, [=](int i) { return ents[i].type == LOG && E::has_collision(av, ents[i], margin); });
+            if (li >= 0) {
                 standing_on_log = true;
-                log_vx = m.vx;
+                log_vx = c.ents[li].vx;
             }
         }
         if (E::get_obj(c, (int)a.x, (int)a.y) == WATER) {

@@ -850,6 +850,8 @@ struct Defaults {
         h.agent_idx = 0;
         h.err = 0;
         h.max_ents_seen = 0;
+        h.max_blits_seen = 0;
+        h.max_rots_seen = 0;
         for (int i = 0; i < GAME_STATE_BYTES; i++) h.game_state[i] = 0;
     }
     static PG_HD void init_constants(Ctx &c) { base_init_constants(c); }

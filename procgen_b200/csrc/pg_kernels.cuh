@@ -14,6 +14,7 @@ struct KParams {
     MT19937 *rng;
     MT19937 *lvl_rng;
     int32_t *scratch;
+    RotBlit *rot_scratch;       // [N][rot_stride] rotated-sprite records of frames too big for shared memory (may be null)
     const GameAssets *assets;   // table of the game this launch handles
     const uint32_t *atlas;
     // libenv-visible buffers (vecgame.cpp:212-268), one slot per env
@@ -29,6 +30,7 @@ struct KParams {
     int32_t ent_stride;         // ent_cap + 1 (ghost slot)
     int32_t grid_stride;
     int32_t scratch_stride;
+    int32_t rot_stride;
     // which envs this launch covers: env = env_first + i * env_step, i in [0, env_count)
     int32_t env_first, env_step, env_count;
     // construction-time options (game.cpp:42-75, vecgame.cpp:284-293)
@@ -53,6 +55,7 @@ PG_HD Ctx make_ctx(const KParams &p, int env) {
     c.ent_cap = p.ent_stride - 1;
     c.grid_cap = p.grid_stride;
     c.scratch_cap = p.scratch_stride;
+    c.rot_scratch_raw = (p.rot_scratch && p.rot_stride > 0) ? (void *)(p.rot_scratch + (size_t)env * p.rot_stride) : nullptr;
     ctx_refresh(c);
     return c;
 }

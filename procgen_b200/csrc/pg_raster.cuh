@@ -62,8 +62,13 @@ template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
 struct FrameT {
     static constexpr int kMaxCells1D = MAX_CELLS_1D;
     static constexpr int kMaxRot = MAX_ROT_BLITS > 0 ? MAX_ROT_BLITS : 1;
+    // Frames of bullet-heavy games would spend most of their shared memory on rotated-sprite
+    // records (208 B each) and fit only 2-3 times per SM; above 32 records they live in the env's
+    // slice of a global scratch array instead (L1/L2 resident while the CTA works on the frame).
+    static constexpr bool kRotInGlobal = MAX_ROT_BLITS > 32;
     int32_t n_rot;
-    RotBlit rot[MAX_ROT_BLITS > 0 ? MAX_ROT_BLITS : 1];
+    RotBlit *rot;
+    RotBlit rot_local[kRotInGlobal ? 1 : kMaxRot];
     static constexpr int kMaxEntBlits = MAX_ENT_BLITS;   // VISIBLE entity blits (after culling)
     Camera cam;
     int32_t low_x, low_y, nx, ny;   // visible grid window: cells [low_x, low_x+nx) x [low_y, low_y+ny)
@@ -1071,6 +1076,11 @@ struct Raster {
             f.n_ent = 0;
             f.n_ent_below = 0;
             f.n_rot = 0;
+            f.rot = Frame::kRotInGlobal ? reinterpret_cast<RotBlit *>(c.rot_scratch_raw) : f.rot_local;
+            if (Frame::kRotInGlobal && c.rot_scratch_raw == nullptr) {
+                h.err |= ERR_SCRATCH_OVERFLOW;
+                f.rot = f.rot_local;
+            }
             if (overflow)
                 h.err |= ERR_BLIT_OVERFLOW;
             if (h.options.use_backgrounds)
@@ -1169,6 +1179,25 @@ struct Raster {
         }
     }
 
+    // Tiles are laid along one axis, so the ones that can touch the device form one contiguous run
+    // [j0, j0 + count): everything else would only produce empty blits. One pixel of guard band
+    // covers the rounding rules.
+    static PG_HD int visible_tiles(const double *r, float tile_ratio, int nt, int &j0) {
+        int first = -1, last = -2;
+        for (int i = 0; i < nt; i++) {
+            double tr[4];
+            tile_rect(r, tile_ratio, nt, i, tr);
+            const bool vis = !(tr[0] + tr[2] < -1 || tr[1] + tr[3] < -1 || tr[0] > RES_W + 1 || tr[1] > RES_H + 1);
+            if (vis) {
+                if (first < 0)
+                    first = i;
+                last = i;
+            }
+        }
+        j0 = first < 0 ? 0 : first;
+        return first < 0 ? 0 : last - first + 1;
+    }
+
     // Blits of entity `ei`: 0 (not drawn / off screen), 1 (normal) or one per tile. `emit(j, blit)`
     // is called for j in [0, count) when `store` is set; returns count.
     template <class Emit>
@@ -1201,16 +1230,18 @@ struct Raster {
             if (r[0] + r[2] < -1 || r[1] + r[3] < -1 || r[0] > RES_W + 1 || r[1] > RES_H + 1)
                 return 0;
             const int nt = tile_count(r, tile_ratio);
+            int j0;
+            const int nvis = visible_tiles(r, tile_ratio, nt, j0);
             if (store) {
-                for (int i = 0; i < nt; i++) {
+                for (int i = 0; i < nvis; i++) {
                     double tr[4];
-                    tile_rect(r, tile_ratio, nt, i, tr);
+                    tile_rect(r, tile_ratio, nt, j0 + i, tr);
                     Blit b;
                     make_sprite_blit_noadjust(c, f, b, tr, o.is_reflected != 0, img_type, o.image_theme, o.alpha);
                     emit(i, b);
                 }
             }
-            return nt;
+            return nvis;
         }
         make_sprite_blit(c, f, single, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
         if (single.kind == BLIT_NONE)
@@ -1235,6 +1266,20 @@ struct Raster {
         tile_rect(r, tile_ratio, nt, j, tr);
         make_sprite_blit_noadjust(c, f, b, tr, o.is_reflected != 0, img_type, o.image_theme, o.alpha);
     }
+    // first visible tile of tiled entity ei (see visible_tiles)
+    static PG_HD int entity_first_visible_tile(Ctx &c, Frame &f, int ei) {
+        const Entity &o = c.ents[ei];
+        double r[4];
+        object_rect(f.cam, o, r);
+        const float tile_ratio = G::get_tile_aspect_ratio(c, ei);
+        const int img_type = G::image_for_type(c, o.image_type);
+        double adj[4];
+        if (G::get_adjusted_image_rect(c, img_type, adj))
+            adjust_rect(r, adj);
+        int j0;
+        visible_tiles(r, tile_ratio, tile_count(r, tile_ratio), j0);
+        return j0;
+    }
 
     // Entities -> blits in draw order (draw_entities z=-1 / 0 / 1, basic-abstract-game.cpp:1059-1066),
     // culled. The whole CTA cooperates (the host harness runs it with one thread): each thread owns
@@ -1250,7 +1295,7 @@ struct Raster {
         // tiled entities (walls drawn as up to ~45 repeats of one sprite): the owner thread only
         // reserves the slots; the tiles themselves are built by all threads afterwards
         constexpr int kMaxTileJobs = 64;
-        __shared__ int job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs];
+        __shared__ int job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs], job_j0[kMaxTileJobs];
         __shared__ int n_jobs;
         const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
         const bool multi_warp = nthreads > 32;
@@ -1311,6 +1356,7 @@ struct Raster {
                                 job_ei[job] = ei;
                                 job_pos[job] = pos;
                                 job_n[job] = mine;
+                                job_j0[job] = entity_first_visible_tile(c, f, ei);
                             } else
 #endif
                             {
@@ -1339,8 +1385,8 @@ struct Raster {
         {
             const int nj = n_jobs < kMaxTileJobs ? n_jobs : kMaxTileJobs;
             for (int job = 0; job < nj; job++) {
-                const int ei = job_ei[job], pos = job_pos[job], nt = job_n[job];
-                for (int j = tid; j < nt; j += nthreads) entity_tile_blit(c, f, ei, j, f.ents[pos + j]);
+                const int ei = job_ei[job], pos = job_pos[job], nt = job_n[job], j0 = job_j0[job];
+                for (int j = tid; j < nt; j += nthreads) entity_tile_blit(c, f, ei, j0 + j, f.ents[pos + j]);
             }
         }
 #endif
@@ -1351,6 +1397,10 @@ struct Raster {
         if (tid == 0) {
             f.n_ent = count;
             f.n_ent_below = below;
+            if (count > c.h->max_blits_seen)
+                c.h->max_blits_seen = count;
+            if (f.n_rot > c.h->max_rots_seen)
+                c.h->max_rots_seen = f.n_rot;
         }
     }
 
@@ -1430,7 +1480,6 @@ struct Raster {
     // A thread shades one pixel column (px fixed, py varies), so everything that depends on the
     // column only is loaded once into a ColumnCtx and reused for all its rows.
     struct ColumnCtx {
-        uint64_t colmask[Frame::kEntWords];
         int nw;          // 64-blit mask words in use this frame: (n_ent + 63) / 64
         int clo, chi;    // grid columns covering this pixel column (255 = none)
         uint32_t bg_sx;  // full-screen background: source column of this pixel column
@@ -1438,8 +1487,6 @@ struct Raster {
     };
     static PG_HD void column_begin(const Frame &f, int px, ColumnCtx &cc) {
         cc.nw = (f.n_ent + 63) >> 6;
-#pragma unroll
-        for (int w = 0; w < Frame::kEntWords; w++) cc.colmask[w] = w < cc.nw ? f.ent_colmask[px][w] : 0;
         cc.clo = 255;
         cc.chi = 0;
         if (G::DRAWS_GRID) {
@@ -1448,6 +1495,24 @@ struct Raster {
         }
         cc.bg_full = f.pad == 1;
         cc.bg_sx = cc.bg_full ? (f.bg[0].basex + (uint32_t)f.bg[0].ix * (uint32_t)px) >> 16 : 0;
+    }
+    // entity blits [lo_bit, hi_bit) of the frame's list that contain the pixel, in list order
+    static PG_HD uint32_t shade_entities(const Frame &f, const ColumnCtx &cc, int px, int py, const uint32_t *atlas, uint32_t dst, int lo_bit,
+                                         int hi_bit) {
+        for (int w = lo_bit >> 6; w < cc.nw && w * 64 < hi_bit; w++) {
+            uint64_t m = f.ent_rowmask[py][w] & f.ent_colmask[px][w];
+            const int lo = lo_bit - w * 64, hi = hi_bit - w * 64;
+            if (lo > 0)
+                m &= ~(((uint64_t)1 << lo) - 1);
+            if (hi < 64)
+                m &= ((uint64_t)1 << hi) - 1;
+            while (m) {
+                const int i = ctz64(m);
+                m &= m - 1;
+                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
+            }
+        }
+        return dst;
     }
     static PG_HD uint32_t shade_pixel(const Frame &f, const ColumnCtx &cc, int px, int py, const uint32_t *atlas) {
         uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
@@ -1458,25 +1523,10 @@ struct Raster {
         } else {
             for (int i = 0; i < f.n_bg; i++) dst = apply_blit(f.bg[i], px, py, dst, atlas, f.rot);
         }
-        uint64_t above[Frame::kEntWords];
+        // entities with render_z == -1 (the first n_ent_below of the list) go under the grid
         const int nb = f.n_ent_below;
-#pragma unroll
-        for (int w = 0; w < Frame::kEntWords; w++) {
-            above[w] = 0;
-            if (w < cc.nw) {
-                uint64_t m = f.ent_rowmask[py][w] & cc.colmask[w];
-                // entities with render_z == -1 go under the grid
-                const int lo = nb - w * 64;
-                const uint64_t below_bits = lo <= 0 ? 0 : (lo >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << lo) - 1));
-                uint64_t mb = m & below_bits;
-                above[w] = m & ~below_bits;
-                while (mb) {
-                    const int i = ctz64(mb);
-                    mb &= mb - 1;
-                    dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
-                }
-            }
-        }
+        if (nb > 0)
+            dst = shade_entities(f, cc, px, py, atlas, dst, 0, nb);
         if (G::DRAWS_GRID) {
             const int rlo = f.row_lo[py], rhi = f.row_hi[py];
             if (cc.clo != 255 && rlo != 255) {
@@ -1485,15 +1535,7 @@ struct Raster {
                         dst = apply_blit(f.cells[ci * f.ny + cj], px, py, dst, atlas, f.rot);
             }
         }
-#pragma unroll
-        for (int w = 0; w < Frame::kEntWords; w++) {
-            uint64_t ma = above[w];
-            while (ma) {
-                const int i = ctz64(ma);
-                ma &= ma - 1;
-                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
-            }
-        }
+        dst = shade_entities(f, cc, px, py, atlas, dst, nb, f.n_ent);
         for (int i = 0; i < f.n_overlay; i++) dst = apply_blit(f.overlay[i], px, py, dst, atlas, f.rot);
         return dst;
     }

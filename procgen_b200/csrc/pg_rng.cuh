@@ -54,6 +54,62 @@ PG_HD uint32_t mt_next(MT19937 &s) {
     return z;
 }
 
+// `count` consecutive raw draws, identical to `count` mt_next() calls. On the device the warp's
+// lanes regenerate and temper up to 32 consecutive state words at a time: word k of a generation
+// depends on the OLD words k, k+1 and on word k+397 (old for k < 227, already NEW otherwise, and
+// then more than 32 positions back), so a batch only has to read everything before it writes.
+PG_HD void rand_fill_raw(MT19937 &s, uint32_t *out, int count) {
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31u);
+    int done = 0;
+    while (done < count) {
+        int p0 = s.p, gen0 = s.gen;
+        __syncwarp();
+        if (p0 >= 624) {
+            p0 = 0;
+            gen0 = 0;
+        }
+        int m = 624 - p0;
+        if (m > 32)
+            m = 32;
+        if (m > count - done)
+            m = count - done;
+        const int k = p0 + lane;
+        const bool act = lane < m;
+        uint32_t v = 0;
+        bool twist = false;
+        if (act) {
+            twist = k >= gen0;
+            if (twist) {
+                const int k1 = (k + 1 == 624) ? 0 : k + 1;
+                const int km = (k + 397 >= 624) ? k + 397 - 624 : k + 397;
+                const uint32_t y = (s.mt[k] & 0x80000000u) | (s.mt[k1] & 0x7fffffffu);
+                v = s.mt[km] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            } else {
+                v = s.mt[k];
+            }
+        }
+        __syncwarp();
+        if (act && twist)
+            s.mt[k] = v;
+        if (act) {
+            uint32_t z = v;
+            z ^= (z >> 11);
+            z ^= (z << 7) & 0x9d2c5680u;
+            z ^= (z << 15) & 0xefc60000u;
+            z ^= (z >> 18);
+            out[done + lane] = z;
+        }
+        s.p = p0 + m;
+        s.gen = (p0 + m > gen0) ? p0 + m : gen0;
+        done += m;
+        __syncwarp();
+    }
+#else
+    for (int i = 0; i < count; i++) out[i] = mt_next(s);
+#endif
+}
+
 // randgen.cpp:6-11
 PG_HD int rand_randint(MT19937 &s, int low, int high) {
     uint32_t x = mt_next(s);

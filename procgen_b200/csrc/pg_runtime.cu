@@ -303,6 +303,7 @@ struct GameVTable {
     const char *name;
     int id;
     int ent_cap, grid_cap, scratch_words;
+    int rot_records;  // rotated-sprite records kept in global memory per env (0 = the frame holds them)
     void (*init)(const KParams &, const LaunchCtx &);
     void (*step)(const KParams &, const LaunchCtx &);
     void (*observe_only)(const KParams &, const LaunchCtx &);
@@ -310,8 +311,8 @@ struct GameVTable {
 
 template <class G>
 GameVTable make_vtable(int id) {
-    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, &launch_env_kernel<G, true>, &launch_env_kernel<G, false>,
-                      &launch_observe_only<G>};
+    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, FrameFor<G>::type::kRotInGlobal ? G::MAX_ROT_BLITS : 0,
+                      &launch_env_kernel<G, true>, &launch_env_kernel<G, false>, &launch_observe_only<G>};
 }
 
 const GameVTable *find_game(const std::string &name) {
@@ -417,6 +418,7 @@ struct VecEnv {
     int max_logic_blocks = 1 << 30;
     // host-buffer (libenv) mode
     bool have_host_bufs = false;
+    bool rgb_copy_enqueued = false;  // this step's observation DMA already follows the render kernels
     bool ob_direct = false;      // caller's obs block is contiguous and page-locked: DMA straight into it
     bool ob_registered = false;
     std::vector<void *> h_ob, h_ac;
@@ -490,6 +492,19 @@ struct VecEnv {
                     games[g]->init(p, lc);
                 else
                     games[g]->step(p, lc);
+#ifndef PG_HOSTSIM
+                // libenv (host buffer) mode: start this chunk's observation DMA right behind its
+                // render kernel, on the same stream, so the copy of one chunk overlaps the kernels
+                // of the next instead of waiting for the whole step (PCIe is the e2e bottleneck:
+                // 12 KiB per env and step)
+                if (have_host_bufs && G == 1 && hi > lo) {
+                    const size_t frame = RES_W * RES_H * 3;
+                    uint8_t *rgb_dst = ob_direct ? (uint8_t *)h_ob[0] : st_rgb;
+                    CUDA_CHECK(cudaMemcpyAsync(rgb_dst + (size_t)lo * frame, base.rgb + (size_t)lo * frame, (size_t)(hi - lo) * frame,
+                                               cudaMemcpyDeviceToHost, lc.stream));
+                    rgb_copy_enqueued = true;
+                }
+#endif
             }
         }
 #ifndef PG_HOSTSIM
@@ -729,8 +744,9 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     fill_tensortypes(v);
 
     // ---- state arrays
-    int ent_cap = 0, grid_cap = 0, scratch_words = 0;
+    int ent_cap = 0, grid_cap = 0, scratch_words = 0, rot_records = 0;
     for (auto g : v->games) {
+        rot_records = std::max(rot_records, g->rot_records);
         ent_cap = std::max(ent_cap, g->ent_cap);
         grid_cap = std::max(grid_cap, g->grid_cap);
         scratch_words = std::max(scratch_words, g->scratch_words);
@@ -746,6 +762,8 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     p.rng = dev_alloc<MT19937>(N);
     p.lvl_rng = dev_alloc<MT19937>(N);
     p.scratch = dev_alloc<int32_t>(N * (size_t)scratch_words);
+    p.rot_stride = rot_records;
+    p.rot_scratch = rot_records > 0 ? dev_alloc<RotBlit>(N * (size_t)rot_records) : nullptr;
     p.atlas = v->d_atlas;
     v->d_action = dev_alloc<int32_t>(N);
     p.action = v->d_action;
@@ -836,7 +854,9 @@ static void fetch_to_host(VecEnv *v) {
     const size_t frame = RES_W * RES_H * 3;
     uint8_t *rgb_dst = v->ob_direct ? (uint8_t *)v->h_ob[0] : v->st_rgb;
 #ifndef PG_HOSTSIM
-    CUDA_CHECK(cudaMemcpyAsync(rgb_dst, p.rgb, N * frame, cudaMemcpyDeviceToHost, v->stream));
+    if (!v->rgb_copy_enqueued)
+        CUDA_CHECK(cudaMemcpyAsync(rgb_dst, p.rgb, N * frame, cudaMemcpyDeviceToHost, v->stream));
+    v->rgb_copy_enqueued = false;
     CUDA_CHECK(cudaMemcpyAsync(v->st_rew, p.rew, N * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
     CUDA_CHECK(cudaMemcpyAsync(v->st_first, p.first, N, cudaMemcpyDeviceToHost, v->stream));
     CUDA_CHECK(cudaMemcpyAsync(v->st_prev_seed, p.info_prev_level_seed, N * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -946,6 +966,8 @@ void libenv_close(libenv_env *handle) {
     dev_free(p.rng);
     dev_free(p.lvl_rng);
     dev_free(p.scratch);
+    if (p.rot_scratch)
+        dev_free(p.rot_scratch);
     dev_free(v->d_atlas);
     dev_free(v->d_action);
     dev_free(p.rgb);
@@ -1169,6 +1191,7 @@ void set_state(libenv_env *handle, int env_idx, char *data, int length) {
     LaunchCtx lc = v->lctx();
     g->observe_only(p, lc);
     v->sync();
+    v->rgb_copy_enqueued = false;  // a DMA started behind the last step predates this frame: observe copies again
 }
 
 int64_t pgb200_kernel_launches(libenv_env *handle) { return ((VecEnv *)handle)->launches; }

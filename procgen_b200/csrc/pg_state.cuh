@@ -122,6 +122,11 @@ struct alignas(16) EnvHdr {
     float min_visibility;
     uint32_t err;           // ErrBits, sticky
     int32_t max_ents_seen;
+    int32_t max_blits_seen; // high-water marks of the frame builder (capacity planning; not game state)
+    int32_t max_rots_seen;
+#ifdef PG_PHASE_TIMING
+    uint32_t dbg_phase[12];  // profiling variant only: SM cycles spent in marked phases of the last reset
+#endif
     // ---- per-game tail (the fields each games/*.cpp class adds)
     alignas(8) unsigned char game_state[GAME_STATE_BYTES];
 };
@@ -156,10 +161,32 @@ struct Ctx {
     int32_t ent_cap;      // list capacity; slot [ent_cap] is the agent ghost slot
     int32_t grid_cap;
     int32_t scratch_cap;  // in int32 words
+    void *rot_scratch_raw; // per-env slice for rotated-sprite records of bullet-heavy frames (render only)
     // register-resident copies of header scalars the physics loop reads constantly; refreshed by
     // ctx_refresh() whenever a game changes them (world size is chosen per episode)
     int32_t mw, mh, oob;
 };
+
+// Profiling variant (-DPG_PHASE_TIMING): PG_PHASE_BEGIN(c) ... PG_PHASE_END(c, id) accumulate cycles.
+#if defined(PG_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define PG_PHASE_BEGIN(c) long long _pg_t0 = clock64()
+#define PG_PHASE_END(c, id)                                              \
+    do {                                                                 \
+        long long _pg_t1 = clock64();                                    \
+        (c).h->dbg_phase[id] += (uint32_t)(_pg_t1 - _pg_t0);             \
+        _pg_t0 = _pg_t1;                                                 \
+    } while (0)
+#define PG_PHASE_RESET(c)                                                \
+    do {                                                                 \
+        for (int _i = 0; _i < 12; _i++) (c).h->dbg_phase[_i] = 0;        \
+    } while (0)
+#define PG_PHASE_NOTE(c, id, v) (c).h->dbg_phase[id] = (uint32_t)(v)
+#else
+#define PG_PHASE_NOTE(c, id, v) do { } while (0)
+#define PG_PHASE_BEGIN(c) do { } while (0)
+#define PG_PHASE_END(c, id) do { } while (0)
+#define PG_PHASE_RESET(c) do { } while (0)
+#endif
 
 PG_HD void ctx_refresh(Ctx &c) {
     c.mw = c.h->main_width;

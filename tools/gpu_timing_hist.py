@@ -6,7 +6,7 @@ import numpy as np, torch
 from procgen_b200 import ProcgenGym3Env
 game = sys.argv[1] if len(sys.argv) > 1 else "coinrun"
 mode = sys.argv[2] if len(sys.argv) > 2 else "easy"
-n = 65536
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
 env = ProcgenGym3Env(n, game, distribution_mode=mode, num_levels=0, rand_seed=0)
 g = torch.Generator(device="cuda").manual_seed(0)
 for t in range(60):
@@ -22,3 +22,14 @@ for name, sel in [("no-reset", ~first), ("reset", first)]:
     if len(c):
         print(name, "n", len(c), "mean %.0f" % c.mean(), "p50 %.0f p90 %.0f p99 %.0f max %.0f cycles" % tuple(np.percentile(c, [50, 90, 99, 100])))
 print("sum cycles / (148 SMs * 48 warps) = %.0f cycles ~ %.2f ms at 1.9 GHz" % (cyc.sum() / (148 * 48), cyc.sum() / (148 * 48) / 1.9e6))
+if os.environ.get("PG_PHASES"):
+    import ctypes as C, struct
+    env._lib.pgb200_debug_read_env.restype = C.c_int
+    buf = (C.c_ubyte * 1024)()
+    idx = np.nonzero(first)[0][:64]
+    acc = np.zeros(12)
+    for e in idx:
+        env._lib.pgb200_debug_read_env(env._h, int(e), buf, None, 0)
+        acc += np.array(struct.unpack_from("<12I", bytes(buf), 240), dtype=np.float64)
+    if len(idx):
+        print("mean cycles per marked phase over", len(idx), "reset envs:", [int(v) for v in acc / len(idx)])
