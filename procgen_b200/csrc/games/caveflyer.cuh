@@ -133,13 +133,11 @@ struct CaveFlyerGame : Defaults<CaveFlyerGame>, DrawDefaults<CaveFlyerGame> {
         }
         int16_t *g = c.grid;
         pg_warp_for(n, [=](int i) { g[i] = (int16_t)WALL_OBJ; });
-        int nfree = 0;
-        for (int i = 0; i < n; i++) {
-            if (best_room[i]) {
-                c.grid[i] = (int16_t)SPACE;
-                free_cells[nfree++] = i;
-            }
-        }
+        pg_warp_for(n, [=](int i) {
+            if (best_room[i])
+                g[i] = (int16_t)SPACE;
+        });
+        int nfree = pg_warp_compact(n, free_cells, [=](int i) { return best_room[i] != 0; });
         simple_choose(c, nfree, 2, chosen, flags);
         int agent_cell = free_cells[chosen[0]];
         int goal_cell = free_cells[chosen[1]];
@@ -166,14 +164,11 @@ struct CaveFlyerGame : Defaults<CaveFlyerGame>, DrawDefaults<CaveFlyerGame> {
 #endif
         }
         for (int q = 0; q < path_len; q++) c.grid[goal_path[q]] = (int16_t)MARKER;
-        nfree = 0;
-        for (int i = 0; i < n; i++) {
-            int o = c.grid[i];
-            if (o == SPACE)
-                free_cells[nfree++] = i;
-            else if (o == WALL_OBJ)
-                c.grid[i] = (int16_t)CAVEWALL;
-        }
+        nfree = pg_warp_compact(n, free_cells, [=](int i) { return g[i] == SPACE; });
+        pg_warp_for(n, [=](int i) {
+            if (g[i] == WALL_OBJ)
+                g[i] = (int16_t)CAVEWALL;
+        });
         int chunk_size = nfree / 80;
         int num_objs = 3 * chunk_size;
         if (num_objs > GRID_CAP) {

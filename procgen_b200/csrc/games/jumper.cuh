@@ -238,18 +238,14 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         }
         int16_t *g = c.grid;
         pg_warp_for(n, [=](int i) { g[i] = (int16_t)CAVEWALL; });
-        int nfree = 0;
-        for (int i = 0; i < n; i++) {
-            if (best_room[i]) {
-                c.grid[i] = (int16_t)SPACE;
-                free_cells[nfree++] = i;
-            }
-        }
+        pg_warp_for(n, [=](int i) {
+            if (best_room[i])
+                g[i] = (int16_t)SPACE;
+        });
+        const int nfree = pg_warp_compact(n, free_cells, [=](int i) { return best_room[i] != 0; });
         int goal_cell = free_cells[rand_randn(rg, nfree)];
-        int ncand = 0;
-        for (int i = 0; i < n; i++)
-            if (is_space_on_ground(c, i % w, i / w))
-                candidates[ncand++] = i;
+        Ctx *cp = &c;
+        const int ncand = pg_warp_compact(n, candidates, [=](int i) { return is_space_on_ground(*cp, i % w, i / w); });
         if (ncand <= 0) {
             h.err |= ERR_FASSERT;
             return;
@@ -271,42 +267,69 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         PG_PHASE_END(c, 7);
         s.goal_idx = E::spawn_entity_at_idx(c, goal_cell, .5, GOAL);
         float spike_prob = h.options.distribution_mode == MemoryMode ? 0 : .2;
-        for (int i = 0; i < n; i++) {
-            int x = i % w;
-            int y = i / w;
-            if (is_space_on_ground(c, x, y) && (is_space_on_ground(c, x - 1, y) && is_space_on_ground(c, x + 1, y))) {
-                if (rand_rand01(rg) < spike_prob)
-                    E::set_obj(c, x, y, SPIKE);
+        // Both loops below walk the cells in order, and what they do at a cell (an RNG draw, a
+        // changed cell) can change the test for later cells only. The warp finds the next cell
+        // that passes the test, handles it exactly as the reference's loop body, and — if the grid
+        // changed — re-tests from the next cell on.
+        {
+            ScanUpIter it(0, n);
+            while (true) {
+                const int i = it.next([=](int k) {
+                    const int x = k % w, y = k / w;
+                    return is_space_on_ground(*cp, x, y) && (is_space_on_ground(*cp, x - 1, y) && is_space_on_ground(*cp, x + 1, y));
+                });
+                if (i < 0)
+                    break;
+                if (rand_rand01(rg) < spike_prob) {
+                    E::set_obj(c, i % w, i / w, SPIKE);
+                    it.restart_from(i + 1);
+                }
             }
         }
         // long vertical walls are broken up (jumper.cpp:323-335)
-        for (int i = 0; i < n; i++) {
-            int x = i % w;
-            int y = i / w;
-            if (is_left_wall(c, x, y) && is_left_wall(c, x, y + 1) && is_left_wall(c, x, y + 2))
-                E::set_obj(c, x, y + rand_randn(rg, 3), SPACE);
-            if (is_right_wall(c, x, y) && is_right_wall(c, x, y + 1) && is_right_wall(c, x, y + 2))
-                E::set_obj(c, x, y + rand_randn(rg, 3), SPACE);
+        {
+            ScanUpIter it(0, n);
+            while (true) {
+                const int i = it.next([=](int k) {
+                    const int x = k % w, y = k / w;
+                    return (is_left_wall(*cp, x, y) && is_left_wall(*cp, x, y + 1) && is_left_wall(*cp, x, y + 2)) ||
+                           (is_right_wall(*cp, x, y) && is_right_wall(*cp, x, y + 1) && is_right_wall(*cp, x, y + 2));
+                });
+                if (i < 0)
+                    break;
+                const int x = i % w, y = i / w;
+                if (is_left_wall(c, x, y) && is_left_wall(c, x, y + 1) && is_left_wall(c, x, y + 2))
+                    E::set_obj(c, x, y + rand_randn(rg, 3), SPACE);
+                if (is_right_wall(c, x, y) && is_right_wall(c, x, y + 1) && is_right_wall(c, x, y + 2))
+                    E::set_obj(c, x, y + rand_randn(rg, 3), SPACE);
+                it.restart_from(i + 1);
+            }
         }
         {
             Entity &a = agent_of(c);
             a.x = (float)((agent_cell % w) + .5);
             a.y = (agent_cell / w) + a.ry;
         }
-        for (int i = 0; i < n; i++) {
-            if (c.grid[i] == SPIKE) {
+        {
+            // get_cells_with_type(SPIKE): ascending cell list (reusing the candidate buffer)
+            const int nspikes = pg_warp_compact(n, candidates, [=](int i) { return g[i] == SPIKE; });
+            for (int q = 0; q < nspikes; q++) {
+                const int i = candidates[q];
                 c.grid[i] = (int16_t)SPACE;
                 float spike_ry = 0.4f;
                 float spike_rx = 0.23f;
                 E::add_entity_rxy(c, (float)((i % w) + .5), (i / w) + spike_ry, 0, 0, spike_rx, spike_ry, SPIKE);
             }
         }
-        for (int i = 0; i < n; i++) {
-            int x = i % w;
-            int y = i / w;
-            if (is_top_wall(c, x, y))
-                E::set_obj(c, x, y, CAVEWALL_TOP);
-        }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        // a wall cell with free space above gets the "top" sprite; turning a cell into a top wall
+        // never changes another cell's test (it stays a non-SPACE cell), so cells are independent
+        pg_warp_for(n, [=](int i) {
+            if (is_top_wall(*cp, i % w, i / w))
+                g[i] = (int16_t)CAVEWALL_TOP;
+        });
         agent_of(c).rx = 0.254f;
         agent_of(c).ry = 0.4f;
         h.out_of_bounds_object = CAVEWALL;

@@ -359,6 +359,32 @@ PG_HD void pg_warp_for(int n, F f) {
 #endif
 }
 
+// out[] = every i in [0, n) with pred(i), ascending (the reference's "for i: if (...) v.push_back(i)");
+// returns the count. pred must be pure. Device: ballot + popcount ranks per 32-index chunk.
+template <class F>
+PG_HD int pg_warp_compact(int n, int32_t *out, F pred) {
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31u);
+    int count = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool hit = (i < n) && pred(i);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit)
+            out[count + __popc(m & ((1u << lane) - 1u))] = i;
+        count += __popc(m);
+    }
+    __syncwarp();
+    return count;
+#else
+    int count = 0;
+    for (int i = 0; i < n; i++)
+        if (pred(i))
+            out[count++] = i;
+    return count;
+#endif
+}
+
 // a[from .. n-2] = a[from+1 .. n-1] for records of `words` int32 each (vector::erase of one element)
 PG_HD void pg_warp_erase(int32_t *a, int from, int n, int words) {
 #if defined(__CUDA_ARCH__)

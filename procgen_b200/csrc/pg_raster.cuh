@@ -86,6 +86,11 @@ struct FrameT {
     uint64_t ent_colmask[RES_W][kEntWords];  //        ... this pixel column
     uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
     uint8_t row_lo[RES_H], row_hi[RES_H];
+    // tiled entities only reserve their blit slots while the list is built; the tiles themselves
+    // are filled in by all threads afterwards (frame_tiles)
+    static constexpr int kMaxTileJobs = 64;
+    int32_t n_jobs;
+    int32_t job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs], job_j0[kMaxTileJobs];
     Blit bg[MAX_BG_BLITS];
     Blit overlay[MAX_OVERLAY_BLITS];
     Blit ents[MAX_ENT_BLITS];
@@ -961,6 +966,9 @@ struct Raster {
         }
         if (y1 < y0)
             return;
+#if defined(__CUDA_ARCH__)
+        f.rot[slot] = rb;  // rows outside [y0, y1] are never read: the blit's box excludes them
+#endif
         b.x1 = (uint8_t)x0;
         b.y1 = (uint8_t)y0;
         b.w = (uint8_t)(x1 - x0);
@@ -1076,6 +1084,7 @@ struct Raster {
             f.n_ent = 0;
             f.n_ent_below = 0;
             f.n_rot = 0;
+            f.n_jobs = 0;
             f.rot = Frame::kRotInGlobal ? reinterpret_cast<RotBlit *>(c.rot_scratch_raw) : f.rot_local;
             if (Frame::kRotInGlobal && c.rot_scratch_raw == nullptr) {
                 h.err |= ERR_SCRATCH_OVERFLOW;
@@ -1292,19 +1301,8 @@ struct Raster {
         int below = 0;
 #if defined(__CUDA_ARCH__)
         __shared__ int warp_tot[32];
-        // tiled entities (walls drawn as up to ~45 repeats of one sprite): the owner thread only
-        // reserves the slots; the tiles themselves are built by all threads afterwards
-        constexpr int kMaxTileJobs = 64;
-        __shared__ int job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs], job_j0[kMaxTileJobs];
-        __shared__ int n_jobs;
         const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
         const bool multi_warp = nthreads > 32;
-        if (tid == 0)
-            n_jobs = 0;
-        if (multi_warp)
-            __syncthreads();
-        else
-            __syncwarp();
 #endif
         for (int z = -1; z <= 1; z++) {
             for (int base = 0; base < n; base += nthreads) {
@@ -1351,12 +1349,12 @@ struct Raster {
                             f.ents[pos] = single;
                         } else {
 #if defined(__CUDA_ARCH__)
-                            const int job = mine > 1 ? atomicAdd(&n_jobs, 1) : kMaxTileJobs;
-                            if (job < kMaxTileJobs) {
-                                job_ei[job] = ei;
-                                job_pos[job] = pos;
-                                job_n[job] = mine;
-                                job_j0[job] = entity_first_visible_tile(c, f, ei);
+                            const int job = mine > 1 ? atomicAdd(&f.n_jobs, 1) : Frame::kMaxTileJobs;
+                            if (job < Frame::kMaxTileJobs) {
+                                f.job_ei[job] = ei;
+                                f.job_pos[job] = pos;
+                                f.job_n[job] = mine;
+                                f.job_j0[job] = entity_first_visible_tile(c, f, ei);
                             } else
 #endif
                             {
@@ -1377,19 +1375,6 @@ struct Raster {
             if (z == -1)
                 below = count;
         }
-#if defined(__CUDA_ARCH__)
-        if (multi_warp)
-            __syncthreads();
-        else
-            __syncwarp();
-        {
-            const int nj = n_jobs < kMaxTileJobs ? n_jobs : kMaxTileJobs;
-            for (int job = 0; job < nj; job++) {
-                const int ei = job_ei[job], pos = job_pos[job], nt = job_n[job], j0 = job_j0[job];
-                for (int j = tid; j < nt; j += nthreads) entity_tile_blit(c, f, ei, j0 + j, f.ents[pos + j]);
-            }
-        }
-#endif
         if (count > Frame::kMaxEntBlits)
             count = Frame::kMaxEntBlits;
         if (below > count)
@@ -1440,6 +1425,15 @@ struct Raster {
             int theme = G::theme_for_grid_obj(c, type);
             double r[4] = {f.col_x[ci], f.row_y[cj], f.cell_w, f.cell_w};
             make_sprite_blit(c, f, b, r, 0, false, type, theme, 1.0f);
+        }
+    }
+
+    // ---- phase C1b (device): the tiles reserved by build_entity_blits, one tile per thread
+    static PG_HD void frame_tiles(Ctx &c, Frame &f, int tid, int nthreads) {
+        const int nj = f.n_jobs < Frame::kMaxTileJobs ? f.n_jobs : Frame::kMaxTileJobs;
+        for (int job = 0; job < nj; job++) {
+            const int ei = f.job_ei[job], pos = f.job_pos[job], nt = f.job_n[job], j0 = f.job_j0[job];
+            for (int j = tid; j < nt; j += nthreads) entity_tile_blit(c, f, ei, j0 + j, f.ents[pos + j]);
         }
     }
 

@@ -201,6 +201,10 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     __syncthreads();
     env_render_build<G, Frame>(p, env, f, tid, kRenderThreads, 32);
     __syncthreads();
+    if (f.n_jobs > 0) {  // block-uniform
+        env_render_tiles<G, Frame>(p, env, f, tid, kRenderThreads);
+        __syncthreads();
+    }
     env_render_masks<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
     env_render_pixels<G, Frame>(p, env, f, tid, kRenderThreads);
