@@ -176,6 +176,9 @@ __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kern
     }
 }
 
+#ifndef PG_RENDER_CTAS_PER_SM
+#define PG_RENDER_CTAS_PER_SM 0  // 0 = as many as registers / the frame allow
+#endif
 // Resident CTAs per SM the render kernel is compiled for. The shader is issue-bound and gains from
 // occupancy (measured: +24 % on coinrun going from 6 to 8 CTAs/SM = 64 registers), but a frame
 // with hundreds of blits does not fit 8 times into shared memory, and there the register cap only
@@ -230,6 +233,7 @@ struct LaunchCtx {
     cudaStream_t stream;
     unsigned int *ticket;     // work counter of this launch slot (one per in-flight logic kernel)
     int max_logic_blocks;     // SM count x resident CTAs per SM
+    int render_smem_floor;    // dynamic shared memory requested per render CTA is at least this (co-residency knob)
     cudaEvent_t *tev;         // optional: 3 events (before logic, between, after render) for kernel timing
 #endif
     int64_t *launch_counter;
@@ -241,10 +245,15 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     if (p.env_count <= 0)
         return;
 #ifndef PG_HOSTSIM
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Frame)));
-        attr_set = true;
+    // Shared memory per render CTA: the frame, or more when the handle asks for fewer resident
+    // render CTAs per SM. At 8 CTAs x 128 threads x 64 registers the render kernel owns the whole
+    // register file of an SM and no logic-kernel block of another env chunk can run beside it;
+    // capping its residency trades a little render speed for real overlap of the two kernels.
+    const int render_smem = (int)sizeof(Frame) > lc.render_smem_floor ? (int)sizeof(Frame) : lc.render_smem_floor;
+    static int attr_set = 0;
+    if (attr_set < render_smem) {
+        CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, render_smem));
+        attr_set = render_smem;
     }
     int logic_blocks = (p.env_count + kLogicEnvsPerBlock - 1) / kLogicEnvsPerBlock;
     if (logic_blocks > lc.max_logic_blocks)
@@ -255,7 +264,7 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, lc.stream>>>(p, lc.ticket);
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
-    render_kernel<G><<<p.env_count, kRenderThreads, sizeof(Frame), lc.stream>>>(p);
+    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
     CUDA_CHECK(cudaGetLastError());
@@ -420,6 +429,7 @@ struct VecEnv {
     static constexpr int kMaxTickets = 64;
     unsigned int *d_tickets = nullptr;
     int max_logic_blocks = 1 << 30;
+    int render_smem_floor = 0;
     // host-buffer (libenv) mode
     bool have_host_bufs = false;
     bool rgb_copy_enqueued = false;  // this step's observation DMA already follows the render kernels
@@ -444,6 +454,7 @@ struct VecEnv {
         lc.stream = stream;
         lc.ticket = d_tickets;
         lc.max_logic_blocks = max_logic_blocks;
+        lc.render_smem_floor = render_smem_floor;
         lc.tev = nullptr;
 #endif
         lc.launch_counter = &launches;
@@ -711,6 +722,19 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, v->device));
         v->max_logic_blocks = prop.multiProcessorCount * PG_LOGIC_MIN_BLOCKS;
+        // tuning knobs (defaults chosen from the sweeps in profiles/): resident logic blocks and
+        // render CTAs per SM
+        if (const char *e = getenv("PGB200_LOGIC_BLOCKS_PER_SM"))
+            if (atoi(e) > 0)
+                v->max_logic_blocks = prop.multiProcessorCount * atoi(e);
+        int render_ctas = PG_RENDER_CTAS_PER_SM;
+        if (const char *e = getenv("PGB200_RENDER_CTAS_PER_SM"))
+            render_ctas = atoi(e);
+        if (render_ctas > 0 && render_ctas < 16) {
+            // usable shared memory per SM is 227 KiB, each CTA also pays 1 KiB of system reserve
+            v->render_smem_floor = (227 * 1024) / render_ctas - 1024 - 16;
+            v->render_smem_floor &= ~15;
+        }
         CUDA_CHECK(cudaMalloc((void **)&v->d_tickets, VecEnv::kMaxTickets * sizeof(unsigned int)));
     }
     // sub_step <-> push_obj recurse to depth 5 on the logic thread
