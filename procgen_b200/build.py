@@ -44,10 +44,12 @@ def build_library(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("PG_NVCC_EXTRA", "").split()
-    cmd = [nvcc, *NVCC_FLAGS, *extra, os.path.join(CSRC, "pg_runtime.cu"), "-o", LIB_PATH, "-lz", "-ldl"]
+    tmp = LIB_PATH + ".building"
+    cmd = [nvcc, *NVCC_FLAGS, *extra, os.path.join(CSRC, "pg_runtime.cu"), "-o", tmp, "-lz", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB_PATH)  # never leave a half-written library where a snapshot could pick it up
     return LIB_PATH
 
 

@@ -239,6 +239,22 @@ struct LaunchCtx {
     int64_t *launch_counter;
 };
 
+#ifndef PG_HOSTSIM
+// Dynamic shared memory of one render CTA (frame, or the co-residency floor) with the kernel's
+// opt-in limit raised to it once.
+template <class G>
+int prepare_render_smem(const LaunchCtx &lc) {
+    using Frame = typename FrameFor<G>::type;
+    const int bytes = (int)sizeof(Frame) > lc.render_smem_floor ? (int)sizeof(Frame) : lc.render_smem_floor;
+    static int attr_set = 0;
+    if (attr_set < bytes) {
+        CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        attr_set = bytes;
+    }
+    return bytes;
+}
+#endif
+
 template <class G, bool INIT>
 void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     using Frame = typename FrameFor<G>::type;
@@ -249,12 +265,7 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     // render CTAs per SM. At 8 CTAs x 128 threads x 64 registers the render kernel owns the whole
     // register file of an SM and no logic-kernel block of another env chunk can run beside it;
     // capping its residency trades a little render speed for real overlap of the two kernels.
-    const int render_smem = (int)sizeof(Frame) > lc.render_smem_floor ? (int)sizeof(Frame) : lc.render_smem_floor;
-    static int attr_set = 0;
-    if (attr_set < render_smem) {
-        CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, render_smem));
-        attr_set = render_smem;
-    }
+    const int render_smem = prepare_render_smem<G>(lc);
     int logic_blocks = (p.env_count + kLogicEnvsPerBlock - 1) / kLogicEnvsPerBlock;
     if (logic_blocks > lc.max_logic_blocks)
         logic_blocks = lc.max_logic_blocks;
@@ -292,9 +303,9 @@ void launch_observe_only(const KParams &p, const LaunchCtx &lc) {
     if (p.env_count <= 0)
         return;
 #ifndef PG_HOSTSIM
-    CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Frame)));
+    const int render_smem = prepare_render_smem<G>(lc);
     camera_kernel<G><<<p.env_count, 32, 0, lc.stream>>>(p);
-    render_kernel<G><<<p.env_count, kRenderThreads, sizeof(Frame), lc.stream>>>(p);
+    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
 #else
     static thread_local Frame *f = new Frame;
