@@ -5,7 +5,7 @@
 // qblendfunctions, qdrawhelper fetchTransformed) — third-party, absent from /root/reference,
 // pinned by the reference at Qt 5.13.2 (procgen-build/procgen_build/build_qt.py:60).  Every rule
 // below is cross-checked bit-for-bit against a real Qt 6.6.3 raster engine by
-// oracle/qt6_backend.cpp + tests/test_oracle_qt6.py.  PARITY UNPINNED against Qt 5.13.2 itself.
+// oracle/shim/qt6_backend.cpp + tests/test_oracle.py.  PARITY UNPINNED against Qt 5.13.2 itself.
 //
 // Rules (SURVEY §8a R1–R4):
 //  F  fillRect(QRectF, opaque): pixels [qRound(x), qRound(x+w)) x [qRound(y), qRound(y+h)).

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE — C entry point that issues, through whichever QPainter backend this
 // library was linked with (restatement or real Qt 6), exactly the call sequence of
 // BasicAbstractGame::draw_image (basic-abstract-game.cpp:877-913) for one sprite. Used by
-// tests/test_oracle_qt6.py to pin the raster rules on synthetic rect / angle / opacity sweeps.
+// tests/test_oracle.py to pin the raster rules on synthetic rect / angle / opacity sweeps.
 #include "qt_shim.h"
 
 extern "C" __attribute__((visibility("default"))) void shim_test_draw_image(

@@ -20,6 +20,7 @@ struct DodgeballGame : Defaults<DodgeballGame>, DrawDefaults<DodgeballGame> {
     static constexpr int MAX_ROT_BLITS = 64;      // everything that faces a direction or spins (measured peak 20)
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "dodgeball";
+    static constexpr bool DEFER_ROTATED = true;
 
     // dodgeball.cpp:8-24
     static constexpr float COMPLETION_BONUS = 10.0f;

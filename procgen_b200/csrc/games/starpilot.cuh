@@ -25,6 +25,7 @@ struct StarpilotGame : Defaults<StarpilotGame>, DrawDefaults<StarpilotGame> {
     static constexpr int MAX_ROT_BLITS = 224;  // ships, bullets and the agent all carry a rotation
     static constexpr int MAX_VIEW_CELLS = 16;
     static constexpr const char *NAME = "starpilot";
+    static constexpr bool DEFER_ROTATED = true;
     static constexpr bool DRAWS_GRID = false;  // entities only; the grid stays all SPACE
 
     // starpilot.cpp:6-26

@@ -163,6 +163,14 @@ PG_HD void env_render_tiles(const KParams &p, int env, Frame &f, int tid, int nt
 }
 
 template <class G, class Frame>
+PG_HD void env_render_rots(const KParams &p, int env, Frame &f, int tid, int nthreads) {
+    if (G::DEFER_ROTATED) {
+        Ctx c = make_ctx(p, env);
+        Raster<G, Frame>::frame_rots(c, f, tid, nthreads);
+    }
+}
+
+template <class G, class Frame>
 PG_HD void env_render_masks(const KParams &p, int env, Frame &f, int tid, int nthreads) {
     Raster<G, Frame>::frame_masks(f, tid, nthreads);
 }

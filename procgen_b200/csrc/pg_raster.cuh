@@ -25,7 +25,8 @@
 
 namespace pg {
 
-enum BlitKind : uint8_t { BLIT_NONE = 0, BLIT_IMAGE = 1, BLIT_SOLID = 2, BLIT_ROTATED = 3, BLIT_SPANS = 4 };
+enum BlitKind : uint8_t { BLIT_NONE = 0, BLIT_IMAGE = 1, BLIT_SOLID = 2, BLIT_ROTATED = 3, BLIT_SPANS = 4,
+                          BLIT_ROT_PENDING = 5 /* slot reserved while the list is built; resolved by frame_rots */ };
 
 struct Blit {
     uint8_t x1, y1, w, h;    // device pixels [x1,x1+w) x [y1,y1+h) after clip + Qt's edge guards;
@@ -886,7 +887,8 @@ struct Raster {
     }
 
     // draw_image (basic-abstract-game.cpp:877-913) for the un-rotated, un-tiled case
-    static PG_HD void make_sprite_blit(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha) {
+    static PG_HD void make_sprite_blit(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
+                                       int defer_ei = -1) {
         blit_clear(b);
         int img_type = G::image_for_type(c, base_type);
         if (img_type < 0)
@@ -940,6 +942,15 @@ struct Raster {
         if (pg_dfabs(m.m12) <= 1e-12 && pg_dfabs(m.m21) <= 1e-12) {
             // QTransform::type() is fuzzy: +-180 degrees is a (mirroring) scale
             make_image_blit(b, m.m11 * r[0] + m.dx, m.m22 * r[1] + m.dy, m.m11 * r[2], m.m22 * r[3], sd, is_reflected, io, f.snap != 0);
+            return;
+        }
+        if (defer_ei >= 0) {
+            // The scan conversion below is long and branchy; done here, by the thread that happens
+            // to own the entity, it would serialise against the (different) code paths its warp
+            // neighbours take for their entities. Reserve the slot and let frame_rots run all
+            // rotated sprites of the frame side by side.
+            b.kind = BLIT_ROT_PENDING;
+            b.src = (uint32_t)defer_ei;
             return;
         }
         int slot;
@@ -1192,15 +1203,23 @@ struct Raster {
     // [j0, j0 + count): everything else would only produce empty blits. One pixel of guard band
     // covers the rounding rules.
     static PG_HD int visible_tiles(const double *r, float tile_ratio, int nt, int &j0) {
+        // same arithmetic as tile_rect, with the per-tile size computed once
+        const bool vertical = tile_ratio < 0;
+        const float step = vertical ? (float)(r[3] / nt) : (float)(r[2] / nt);
+        const double origin = vertical ? r[1] : r[0];
+        const double limit = vertical ? RES_H + 1 : RES_W + 1;
+        // the other axis is the same for every tile
+        const bool cross_visible = vertical ? !(r[0] + (double)(float)r[2] < -1 || r[0] > RES_W + 1) : !(r[1] + (double)(float)r[3] < -1 || r[1] > RES_H + 1);
         int first = -1, last = -2;
-        for (int i = 0; i < nt; i++) {
-            double tr[4];
-            tile_rect(r, tile_ratio, nt, i, tr);
-            const bool vis = !(tr[0] + tr[2] < -1 || tr[1] + tr[3] < -1 || tr[0] > RES_W + 1 || tr[1] > RES_H + 1);
-            if (vis) {
-                if (first < 0)
-                    first = i;
-                last = i;
+        if (cross_visible) {
+            for (int i = 0; i < nt; i++) {
+                const double lo = origin + (double)(step * i);
+                const bool vis = !(lo + (double)step < -1 || lo > limit);
+                if (vis) {
+                    if (first < 0)
+                        first = i;
+                    last = i;
+                }
             }
         }
         j0 = first < 0 ? 0 : first;
@@ -1252,7 +1271,11 @@ struct Raster {
             }
             return nvis;
         }
+#if defined(__CUDA_ARCH__)
+        make_sprite_blit(c, f, single, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha, G::DEFER_ROTATED ? ei : -1);
+#else
         make_sprite_blit(c, f, single, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
+#endif
         if (single.kind == BLIT_NONE)
             return 0;
         if (store)
@@ -1434,6 +1457,22 @@ struct Raster {
         for (int job = 0; job < nj; job++) {
             const int ei = f.job_ei[job], pos = f.job_pos[job], nt = f.job_n[job], j0 = f.job_j0[job];
             for (int j = tid; j < nt; j += nthreads) entity_tile_blit(c, f, ei, j0 + j, f.ents[pos + j]);
+        }
+    }
+
+    // ---- phase C1c (device): rotated sprites whose slots build_entity_blits reserved
+    static PG_HD void frame_rots(Ctx &c, Frame &f, int tid, int nthreads) {
+        const int n = f.n_ent;
+        for (int i = tid; i < n; i += nthreads) {
+            if (f.ents[i].kind != BLIT_ROT_PENDING)
+                continue;
+            const int ei = (int)f.ents[i].src;
+            const Entity &o = c.ents[ei];
+            double r[4];
+            object_rect(f.cam, o, r);
+            Blit nb;
+            make_sprite_blit(c, f, nb, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
+            f.ents[i] = nb;
         }
     }
 

@@ -200,17 +200,38 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     Frame &f = *reinterpret_cast<Frame *>(smem_raw);
     const int env = p.env_first + (int)blockIdx.x * p.env_step;
     const int tid = (int)threadIdx.x;
+#ifdef PG_PHASE_TIMING
+    long long t0 = clock64(), t1;
+#define PG_RENDER_PHASE(id)                                       \
+    do {                                                          \
+        t1 = clock64();                                           \
+        if (tid == 0)                                             \
+            p.hdr[env].dbg_phase[id] = (uint32_t)(t1 - t0);       \
+        t0 = t1;                                                  \
+    } while (0)
+#else
+#define PG_RENDER_PHASE(id) do { } while (0)
+#endif
     env_render_begin<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
+    PG_RENDER_PHASE(8);
     env_render_build<G, Frame>(p, env, f, tid, kRenderThreads, 32);
     __syncthreads();
+    PG_RENDER_PHASE(9);
     if (f.n_jobs > 0) {  // block-uniform
         env_render_tiles<G, Frame>(p, env, f, tid, kRenderThreads);
         __syncthreads();
     }
+    if (G::DEFER_ROTATED) {  // compile-time, per game
+        env_render_rots<G, Frame>(p, env, f, tid, kRenderThreads);
+        __syncthreads();
+    }
     env_render_masks<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
+    PG_RENDER_PHASE(10);
     env_render_pixels<G, Frame>(p, env, f, tid, kRenderThreads);
+    PG_RENDER_PHASE(11);
+#undef PG_RENDER_PHASE
 }
 #endif
 

@@ -2,7 +2,8 @@
 mkdir -p gpurun_out
 : > gpurun_out/knobs.jsonl
 if [ "${RUN_TESTS:-1}" = "1" ]; then timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "libenv_host_buffers or sixteen" 2>&1 | tail -3; fi
-for k in ${KNOBS:-"0:24 7:24 6:24 5:24 0:12 6:12 6:8 5:8"}; do
+KNOBS=${KNOBS:-0:24 7:24 6:24 5:24 0:12 6:12 6:16 5:16}
+for k in $KNOBS; do
   export PGB200_RENDER_CTAS_PER_SM=${k%%:*} PGB200_LOGIC_BLOCKS_PER_SM=${k##*:}
   for g in ${GAMES:-coinrun65k}; do
     m=hard; e=${GAME_ENVS:-32768}

@@ -26,7 +26,7 @@ if os.environ.get("PG_PHASES"):
     import ctypes as C, struct
     env._lib.pgb200_debug_read_env.restype = C.c_int
     buf = (C.c_ubyte * 1024)()
-    idx = np.nonzero(first)[0][:64]
+    idx = np.nonzero(first)[0][:64] if not os.environ.get("PG_PHASES_ALL") else np.arange(0, n, max(1, n // 256))
     acc = np.zeros(12)
     for e in idx:
         env._lib.pgb200_debug_read_env(env._h, int(e), buf, None, 0)
