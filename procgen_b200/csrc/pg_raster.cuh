@@ -602,7 +602,11 @@ PG_HD uint32_t blend_px(uint32_t dst, uint32_t src, int int_opacity) {
     return dst;
 }
 
+#if defined(PG_APPLY_NOINLINE) && defined(__CUDACC__)
+__host__ __device__ __noinline__ uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uint32_t *atlas, const RotBlit *rots) {
+#else
 PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uint32_t *atlas, const RotBlit *rots) {
+#endif
     const uint32_t box = *reinterpret_cast<const uint32_t *>(&b);  // x1 | y1<<8 | w<<16 | h<<24
     const uint32_t dx = (uint32_t)px - (box & 0xffu);
     const uint32_t dy = (uint32_t)py - ((box >> 8) & 0xffu);
