@@ -252,6 +252,8 @@ __global__ void camera_kernel(KParams p) {
 struct LaunchCtx {
 #ifndef PG_HOSTSIM
     cudaStream_t stream;
+    cudaStream_t logic_stream;  // null, or a higher-priority stream the logic kernel goes to (then `link` orders render behind it)
+    cudaEvent_t link;
     unsigned int *ticket;     // work counter of this launch slot (one per in-flight logic kernel)
     int max_logic_blocks;     // SM count x resident CTAs per SM
     int render_smem_floor;    // dynamic shared memory requested per render CTA is at least this (co-residency knob)
@@ -290,10 +292,15 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     int logic_blocks = (p.env_count + kLogicEnvsPerBlock - 1) / kLogicEnvsPerBlock;
     if (logic_blocks > lc.max_logic_blocks)
         logic_blocks = lc.max_logic_blocks;
-    CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, sizeof(unsigned int), lc.stream));
+    cudaStream_t ls = lc.logic_stream ? lc.logic_stream : lc.stream;
+    CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, sizeof(unsigned int), ls));
     if (lc.tev)
-        CUDA_CHECK(cudaEventRecord(lc.tev[0], lc.stream));
-    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, lc.stream>>>(p, lc.ticket);
+        CUDA_CHECK(cudaEventRecord(lc.tev[0], ls));
+    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, ls>>>(p, lc.ticket);
+    if (lc.logic_stream) {
+        CUDA_CHECK(cudaEventRecord(lc.link, ls));
+        CUDA_CHECK(cudaStreamWaitEvent(lc.stream, lc.link, 0));
+    }
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
     render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
@@ -447,6 +454,11 @@ struct VecEnv {
     cudaStream_t own_stream = nullptr;
     static constexpr int kAuxStreams = PG_AUX_STREAMS;
     cudaStream_t aux[kAuxStreams] = {};
+    // PGB200_PRIORITY_SPLIT=1: logic kernels go to high-priority twins of the auxiliary streams so
+    // their (small) blocks are dispatched ahead of the render CTAs queued by other chunks
+    bool priority_split = false;
+    cudaStream_t aux_hi[kAuxStreams] = {};
+    cudaEvent_t ev_link[kAuxStreams] = {};
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[kAuxStreams] = {};
     // optional per-launch kernel timing (pgb200_kernel_timing_begin/end): a pool of event triples
@@ -484,6 +496,8 @@ struct VecEnv {
         LaunchCtx lc;
 #ifndef PG_HOSTSIM
         lc.stream = stream;
+        lc.logic_stream = nullptr;
+        lc.link = nullptr;
         lc.ticket = d_tickets;
         lc.max_logic_blocks = max_logic_blocks;
         lc.render_smem_floor = render_smem_floor;
@@ -509,7 +523,11 @@ struct VecEnv {
         const int nstreams = (chunks * G > 1 && !serialize_launches) ? kAuxStreams : 0;
         if (nstreams) {
             CUDA_CHECK(cudaEventRecord(ev_fork, stream));
-            for (int s = 0; s < nstreams; s++) CUDA_CHECK(cudaStreamWaitEvent(aux[s], ev_fork, 0));
+            for (int s = 0; s < nstreams; s++) {
+                CUDA_CHECK(cudaStreamWaitEvent(aux[s], ev_fork, 0));
+                if (priority_split)
+                    CUDA_CHECK(cudaStreamWaitEvent(aux_hi[s], ev_fork, 0));
+            }
         }
 #endif
         int k = 0;
@@ -526,8 +544,13 @@ struct VecEnv {
                 p.env_count = hi - lo;
                 LaunchCtx lc = lctx();
 #ifndef PG_HOSTSIM
-                if (nstreams)
+                if (nstreams) {
                     lc.stream = aux[k % nstreams];
+                    if (priority_split) {
+                        lc.logic_stream = aux_hi[k % nstreams];
+                        lc.link = ev_link[k % nstreams];
+                    }
+                }
                 lc.ticket = d_tickets + (k % kMaxTickets);
                 if (timing && tev_used + 3 <= tev_pool.size()) {
                     lc.tev = &tev_pool[tev_used];
@@ -745,9 +768,19 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     v->set_device();
     CUDA_CHECK(cudaStreamCreateWithFlags(&v->own_stream, cudaStreamNonBlocking));
     v->stream = v->own_stream;
+    {
+        const char *e = getenv("PGB200_PRIORITY_SPLIT");
+        v->priority_split = e && atoi(e) != 0;
+    }
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = higher priority
     for (int s = 0; s < VecEnv::kAuxStreams; s++) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&v->aux[s], cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&v->ev_join[s], cudaEventDisableTiming));
+        if (v->priority_split) {
+            CUDA_CHECK(cudaStreamCreateWithPriority(&v->aux_hi[s], cudaStreamNonBlocking, prio_hi));
+            CUDA_CHECK(cudaEventCreateWithFlags(&v->ev_link[s], cudaEventDisableTiming));
+        }
     }
     CUDA_CHECK(cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming));
     {
@@ -1057,6 +1090,10 @@ void libenv_close(libenv_env *handle) {
     for (int s = 0; s < VecEnv::kAuxStreams; s++) {
         if (v->aux[s])
             cudaStreamDestroy(v->aux[s]);
+        if (v->aux_hi[s])
+            cudaStreamDestroy(v->aux_hi[s]);
+        if (v->ev_link[s])
+            cudaEventDestroy(v->ev_link[s]);
         if (v->ev_join[s])
             cudaEventDestroy(v->ev_join[s]);
     }

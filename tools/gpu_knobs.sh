@@ -4,11 +4,12 @@ mkdir -p gpurun_out
 if [ "${RUN_TESTS:-1}" = "1" ]; then timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "libenv_host_buffers or sixteen" 2>&1 | tail -3; fi
 KNOBS=${KNOBS:-0:24 7:24 6:24 5:24 0:12 6:12 6:16 5:16}
 for k in $KNOBS; do
-  export PGB200_RENDER_CTAS_PER_SM=${k%%:*} PGB200_LOGIC_BLOCKS_PER_SM=${k##*:}
+  IFS=: read R L P <<< "$k"
+  export PGB200_RENDER_CTAS_PER_SM=$R PGB200_LOGIC_BLOCKS_PER_SM=$L PGB200_PRIORITY_SPLIT=${P:-0}
   for g in ${GAMES:-coinrun65k}; do
     m=hard; e=${GAME_ENVS:-32768}
     if [ "$g" = "coinrun65k" ]; then g=coinrun; m=easy; e=65536; fi
-    timeout 300 python bench.py --game $g --mode $m --envs-per-gpu $e --steps 40 --warmup 8 --no-e2e --no-cpu-baseline 2>> gpurun_out/knobs.err | sed "s/^{/{\"variant\": \"R$PGB200_RENDER_CTAS_PER_SM-L$PGB200_LOGIC_BLOCKS_PER_SM\", /" >> gpurun_out/knobs.jsonl
+    timeout 300 python bench.py --game $g --mode $m --envs-per-gpu $e --steps 40 --warmup 8 --no-e2e --no-cpu-baseline 2>> gpurun_out/knobs.err | sed "s/^{/{\"variant\": \"R$PGB200_RENDER_CTAS_PER_SM-L$PGB200_LOGIC_BLOCKS_PER_SM-P$PGB200_PRIORITY_SPLIT\", /" >> gpurun_out/knobs.jsonl
   done
 done
 tail -3 gpurun_out/knobs.err
