@@ -1538,6 +1538,8 @@ struct Raster {
                                          int hi_bit) {
         for (int w = lo_bit >> 6; w < cc.nw && w * 64 < hi_bit; w++) {
             uint64_t m = f.ent_rowmask[py][w] & f.ent_colmask[px][w];
+            if (m == 0)
+                continue;  // the common case: no entity blit over this pixel
             const int lo = lo_bit - w * 64, hi = hi_bit - w * 64;
             if (lo > 0)
                 m &= ~(((uint64_t)1 << lo) - 1);
