@@ -47,6 +47,7 @@ struct Climber : Defaults<Climber>, DrawDefaults<Climber> {
     }
     static PG_HD int theme_for_grid_obj(Ctx &c, int type) { return is_wall(type) ? st(c).wall_theme : 0; }
     static PG_HD bool will_reflect(Ctx &c, int src, int target) { return (src == ENEMY && (is_wall(target) || target == ENEMY_BARRIER)); }
+    static PG_HD bool may_be_obstacle(Ctx &c, int target) { return may_block_or_reflect(c, 0, target); }
     static PG_HD bool may_block_or_reflect(Ctx &c, int src, int target) {
         return target == WALL_OBJ || target == c.oob || is_wall(target) || target == ENEMY_BARRIER;
     }

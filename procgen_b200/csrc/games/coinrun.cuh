@@ -66,6 +66,7 @@ struct CoinRun : Defaults<CoinRun>, DrawDefaults<CoinRun> {
     }
     // is_blocked_ents (:187-203) can only be true for CRATE or a type is_blocked accepts; will_reflect
     // (:140-142) only for wall-like types. Entity types here: PLAYER, SAW, ENEMY, CRATE, TRAIL.
+    static PG_HD bool may_be_obstacle(Ctx &c, int target) { return may_block_or_reflect(c, 0, target); }
     static PG_HD bool may_block_or_reflect(Ctx &c, int src, int target) {
         return target == CRATE || target == WALL_OBJ || target == c.oob || is_wall(target) || target == ENEMY_BARRIER;
     }

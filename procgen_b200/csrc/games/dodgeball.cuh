@@ -52,6 +52,7 @@ struct DodgeballGame : Defaults<DodgeballGame>, DrawDefaults<DodgeballGame> {
     }
     // no entity ever carries WALL_OBJ or the out-of-bounds id, so entity overlaps only matter for
     // an enemy bouncing off lava
+    static PG_HD bool may_be_obstacle(Ctx &c, int target) { return target == LAVA_WALL; }
     static PG_HD bool may_block_or_reflect(Ctx &c, int src, int target) { return src == ENEMY && target == LAVA_WALL; }
     // dodgeball.cpp:102-118
     static PG_HD void handle_agent_collision(Ctx &c, int oi) {

@@ -70,6 +70,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
         return false;
     }
     // no entity carries a wall id: entity overlaps never block or reflect (jumper.cpp:111-118, 177-179)
+    static PG_HD bool may_be_obstacle(Ctx &c, int target) { return false; }
     static PG_HD bool may_block_or_reflect(Ctx &c, int src, int target) { return false; }
     // jumper.cpp:120-135
     static PG_HD int image_for_type(Ctx &c, int type) {

@@ -402,7 +402,7 @@ struct Engine {
         // reference: for i = n-1..0 { skip self/erased; if (has_collision) {...} } — the test runs
         // warp-wide, the (rare) hits are handled one at a time in descending order, and the scan
         // restarts below each hit because handling may have moved things.
-        ScanDownIter it(c.h->n_ents);
+        ScanDownIter it((c.obst_hi >= 0 && c.obst_hi < c.h->n_ents) ? c.obst_hi : c.h->n_ents);
         while (true) {
             const Entity *ents = c.ents;
             const float ox = obj.x, oy = obj.y, orx = obj.rx, ory = obj.ry;  // hoisted: warp-uniform
@@ -508,6 +508,12 @@ struct Engine {
     // stepped by the warp's lanes in parallel; smart entities keep their place in the order.
     static PG_HD void step_entities(Ctx &c) {
         int hi = c.h->n_ents;
+        {
+            // no entity is added, erased, moved in the list or re-typed while entities are stepped
+            Ctx *cp = &c;
+            const Entity *ents0 = c.ents;
+            c.obst_hi = 1 + pg_scan_down(hi, [=](int k) { return G::may_be_obstacle(*cp, ents0[k].type); });
+        }
         while (hi > 0) {
             Entity *ents = c.ents;
             const int s = pg_scan_down(hi, [=](int k) { return ents[k].smart_step != 0; });
@@ -519,6 +525,7 @@ struct Engine {
             entity_step(c.ents[s]);
             hi = s;
         }
+        c.obst_hi = -1;
     }
 
     // basic-abstract-game.cpp:145-165
@@ -649,6 +656,8 @@ struct Engine {
     // basic-abstract-game.cpp:686-746
     static PG_HD void basic_game_step(Ctx &c) {
         EnvHdr &h = *c.h;
+        PG_PHASE_RESET(c);
+        PG_PHASE_BEGIN(c);
         h.step_rand_int = rand_randint(*c.rng, 0, 1000000);
         h.move_action = h.action % 9;
         h.special_action = 0;
@@ -674,7 +683,9 @@ struct Engine {
             a.vrot += MIXRATEROT * MAXVTHETA * h.action_vrot;
         }
 
+        PG_PHASE_END(c, 0);
         step_entities(c);
+        PG_PHASE_END(c, 1);
 
         // collision pass (:719-741): entities that need any work are found warp-wide; each is then
         // processed exactly as the reference's loop body, in descending order.
@@ -706,8 +717,11 @@ struct Engine {
                 check_grid_collisions(c, i);
         }
 
+        PG_PHASE_END(c, 2);
         erase_if_needed(c);
         h.done = h.done || is_out_of_bounds(c, agent_of(c));
+        PG_PHASE_END(c, 3);
+        PG_PHASE_NOTE(c, 4, h.n_ents);
     }
 
     // basic-abstract-game.cpp:758-797
@@ -871,6 +885,12 @@ struct Defaults {
     // PURE, conservative pre-filter for sub_step's entity scan: false only if an overlap between
     // entities of these two types can never make is_blocked_ents or will_reflect return true.
     static PG_HD bool may_block_or_reflect(Ctx &c, int src_type, int target_type) { return true; }
+    // PURE, conservative: false only if NO source type can be blocked or reflected by an entity of
+    // this type (may_block_or_reflect(s, target_type) is false for every s). step_entities uses it
+    // to bound sub_step's entity scans to the list prefix that contains such entities at all — in
+    // coinrun only crates qualify, and they sit in front of the hundreds of trail entities that a
+    // level with many enemies accumulates.
+    static PG_HD bool may_be_obstacle(Ctx &c, int target_type) { return true; }
     static PG_HD float get_agent_acceleration_scale(Ctx &c) { return 1.0; }
     static PG_HD void handle_agent_collision(Ctx &c, int obj) {}
     static PG_HD void handle_grid_collision(Ctx &c, int obj, int type, int i, int j) {}

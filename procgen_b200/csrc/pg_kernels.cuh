@@ -55,6 +55,7 @@ PG_HD Ctx make_ctx(const KParams &p, int env) {
     c.ent_cap = p.ent_stride - 1;
     c.grid_cap = p.grid_stride;
     c.scratch_cap = p.scratch_stride;
+    c.obst_hi = -1;
     c.rot_scratch_raw = (p.rot_scratch && p.rot_stride > 0) ? (void *)(p.rot_scratch + (size_t)env * p.rot_stride) : nullptr;
     ctx_refresh(c);
     return c;

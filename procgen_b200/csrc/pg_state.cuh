@@ -165,6 +165,9 @@ struct Ctx {
     // register-resident copies of header scalars the physics loop reads constantly; refreshed by
     // ctx_refresh() whenever a game changes them (world size is chosen per episode)
     int32_t mw, mh, oob;
+    // while step_entities runs: entities at or beyond this index can never block or reflect
+    // anything (Defaults::may_be_obstacle); -1 = not known, scan the whole list
+    int32_t obst_hi;
 };
 
 // Profiling variant (-DPG_PHASE_TIMING): PG_PHASE_BEGIN(c) ... PG_PHASE_END(c, id) accumulate cycles.

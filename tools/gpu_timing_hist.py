@@ -33,3 +33,23 @@ if os.environ.get("PG_PHASES"):
         acc += np.array(struct.unpack_from("<12I", bytes(buf), 240), dtype=np.float64)
     if len(idx):
         print("mean cycles per marked phase over", len(idx), "reset envs:", [int(v) for v in acc / len(idx)])
+
+if os.environ.get("PG_SLOWEST"):
+    import ctypes as C, struct
+    env._lib.pgb200_debug_read_env.restype = C.c_int
+    buf = (C.c_ubyte * 1024)()
+    order = np.argsort(-cyc.astype(np.int64))
+    print("slowest non-reset envs: cycles | phases [pre, step_entities, collisions, erase] n_ents")
+    shown = 0
+    for e in order:
+        if first[e]:
+            continue
+        env._lib.pgb200_debug_read_env(env._h, int(e), buf, None, 0)
+        ph = struct.unpack_from("<12I", bytes(buf), 240)
+        print(int(cyc[e]), ph[:5])
+        shown += 1
+        if shown >= 12:
+            break
+    med = np.argsort(cyc)[len(cyc) // 2]
+    env._lib.pgb200_debug_read_env(env._h, int(med), buf, None, 0)
+    print("median env:", int(cyc[med]), struct.unpack_from("<12I", bytes(buf), 240)[:5])
