@@ -19,6 +19,9 @@ struct BigFish : Defaults<BigFish>, DrawDefaults<BigFish> {
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "bigfish";
     static constexpr bool DRAWS_GRID = false;  // entities only; the grid stays all SPACE
+    // is_blocked / is_blocked_ents / will_reflect are the engine defaults here: only an entity typed WALL_OBJ or as the out-of-bounds object could block
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // bigfish.cpp:8-16
     static constexpr int COMPLETION_BONUS = 10;

@@ -24,6 +24,9 @@ struct BossfightGame : Defaults<BossfightGame>, DrawDefaults<BossfightGame> {
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "bossfight";
     static constexpr bool DRAWS_GRID = false;  // entities only; the grid stays all SPACE
+    // is_blocked / is_blocked_ents / will_reflect are the engine defaults here: only an entity typed WALL_OBJ or as the out-of-bounds object could block
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // bossfight.cpp:8-30
     static constexpr int COMPLETION_BONUS = 10, POSITIVE_REWARD = 1;

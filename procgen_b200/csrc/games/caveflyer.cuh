@@ -14,6 +14,9 @@ struct CaveFlyerGame : Defaults<CaveFlyerGame>, DrawDefaults<CaveFlyerGame> {
     static constexpr int MAX_ROT_BLITS = 32;
     static constexpr int MAX_VIEW_CELLS = 20;  // visibility 16 centred
     static constexpr const char *NAME = "caveflyer";
+    // superset of the types is_blocked (:49-55) and will_reflect (:80) accept
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob || t == CAVEWALL; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // caveflyer.cpp:9-20
     static constexpr float GOAL_REWARD = 10.0f;

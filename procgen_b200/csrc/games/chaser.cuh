@@ -21,6 +21,9 @@ struct ChaserGame : Defaults<ChaserGame>, DrawDefaults<ChaserGame> {
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 19;
     static constexpr const char *NAME = "chaser";
+    // superset of the types is_blocked accepts; nothing reflects
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob || t == MAZE_WALL; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // chaser.cpp:10-23
     static constexpr float ORB_REWARD = 0.04f;

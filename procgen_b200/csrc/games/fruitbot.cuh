@@ -18,6 +18,9 @@ struct FruitBotGame : Defaults<FruitBotGame>, DrawDefaults<FruitBotGame> {
     static constexpr int MAX_ROT_BLITS = 2;
     static constexpr int MAX_VIEW_CELLS = 24;
     static constexpr const char *NAME = "fruitbot";
+    // superset of the types is_blocked and will_reflect accept (barriers are entities)
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob || t == OUT_OF_BOUNDS_WALL || t == BARRIER; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // fruitbot.cpp:8-23
     static constexpr float COMPLETION_BONUS = 10.0;

@@ -20,6 +20,9 @@ struct HeistGame : Defaults<HeistGame>, DrawDefaults<HeistGame> {
     static constexpr int MAX_ROT_BLITS = 8;
     static constexpr int MAX_VIEW_CELLS = 13;    // hard: whole 13x13 world; memory mode is centred (11)
     static constexpr const char *NAME = "heist";
+    // locked doors are entities and block without their key (is_blocked_ents); otherwise the defaults
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob || t == LOCKED_DOOR; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // heist.cpp:10-15
     static constexpr float COMPLETION_BONUS = 10.0f;

@@ -23,6 +23,9 @@ struct LeaperGame : Defaults<LeaperGame>, DrawDefaults<LeaperGame> {
     static constexpr int MAX_ROT_BLITS = 4;
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "leaper";
+    // is_blocked / is_blocked_ents / will_reflect are the engine defaults here: only an entity typed WALL_OBJ or as the out-of-bounds object could block
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // leaper.cpp:6-22
     static constexpr int LOG = 1, ROAD = 2, WATER = 3, CAR = 4, FINISH_LINE = 5;

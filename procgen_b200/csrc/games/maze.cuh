@@ -19,6 +19,9 @@ struct MazeGame : Defaults<MazeGame>, DrawDefaults<MazeGame> {
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 25;    // hard: whole 25x25 world; memory mode is centred (11)
     static constexpr const char *NAME = "maze";
+    // is_blocked / is_blocked_ents / will_reflect are the engine defaults here: only an entity typed WALL_OBJ or as the out-of-bounds object could block
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     static constexpr float REWARD = 10.0;
     static constexpr int GOAL = 2;

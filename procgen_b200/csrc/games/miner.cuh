@@ -17,6 +17,9 @@ struct MinerGame : Defaults<MinerGame>, DrawDefaults<MinerGame> {
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 20;  // hard: whole 20x20 world; memory mode is centred (11)
     static constexpr const char *NAME = "miner";
+    // superset of the types is_blocked and will_reflect accept
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob || t == OOB_WALL || t == BOULDER || t == MOVING_BOULDER || t == DIAMOND || t == MOVING_DIAMOND; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // miner.cpp:8-19
     static constexpr float COMPLETION_BONUS = 10.0;

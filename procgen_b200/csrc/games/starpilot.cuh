@@ -27,6 +27,9 @@ struct StarpilotGame : Defaults<StarpilotGame>, DrawDefaults<StarpilotGame> {
     static constexpr const char *NAME = "starpilot";
     static constexpr bool DEFER_ROTATED = true;
     static constexpr bool DRAWS_GRID = false;  // entities only; the grid stays all SPACE
+    // is_blocked / is_blocked_ents / will_reflect are the engine defaults here: only an entity typed WALL_OBJ or as the out-of-bounds object could block
+    static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob; }
+    static PG_HD bool may_block_or_reflect(Ctx &c, int src, int t) { return may_be_obstacle(c, t); }
 
     // starpilot.cpp:6-26
     static constexpr float V_SCALE = 2.0f / 5.0f;
