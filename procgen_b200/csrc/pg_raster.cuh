@@ -6,20 +6,26 @@
 //
 // Raster rules (Qt raster engine, non-antialiased, restated; see oracle/shim/qt_raster.cpp for
 // the CPU twin and DESIGN.md for how they are pinned against real Qt 6.6.3):
-//   F fillRect -> [qRound(x), qRound(x+w)) x [qRound(y), qRound(y+h))
+//   F fillRect -> [qRound(x), qRound(x+w)) x [qRound(y), qRound(y+h)), qRound = half away from zero
 //   S scaled drawImage -> nearest neighbour, 16.16 fixed point, target snapped to ints (switch)
 //   B src-over with BYTE_MUL; O opacity int(o*256) -> (io*255)>>8
+//   R rotated drawImage -> per-row spans from Qt's scan converter + 16.16 texel stepping (two paths)
+//   E / L drawEllipse (integer midpoint) and cosmetic drawLine, as per-row spans (jumper compass)
 //
 // Phases (render kernel: one CTA per env; `tid`/`nthreads` are explicit so the same code runs in
 // the host debug harness with nthreads = 1; a barrier separates consecutive phases):
 //   prepare_camera   logic thread  prepare_for_drawing -> env header (runs in the logic kernel)
 //   frame_begin      all threads   thread 0: window + background/overlay blits; threads i<nx / j<ny:
 //                                  geometry + pixel span of grid column i / row j
-//   frame_build      all threads   entities -> blits (one entity per thread and round), culled and compacted in draw order with
-//                                  warp ballots; other warps: one blit per visible grid cell and the
-//                                  pixel-column/row -> cell lookup tables (fp64 math happens here,
-//                                  once per sprite instead of once per pixel)
-//   shade_pixel      all threads   the gather
+//   frame_build      all threads   entities -> blits, one entity per thread and round, culled and
+//                                  compacted in draw order with a block-wide prefix sum (few
+//                                  entities: warp 0 alone while the other warps build one blit per
+//                                  visible grid cell and the pixel-column/row -> cell lookups; fp64
+//                                  math happens here, once per sprite instead of once per pixel)
+//   frame_tiles      all threads   tiles of tiled entities whose slots frame_build reserved
+//   frame_rots       all threads   (games with DEFER_ROTATED) rotated sprites whose slots were reserved
+//   frame_masks      all threads   per pixel row / column bit masks of the entity blits
+//   shade_pixel      all threads   the gather, one pixel column per thread
 #pragma once
 #include "pg_engine.cuh"
 
