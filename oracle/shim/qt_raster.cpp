@@ -35,6 +35,13 @@ static inline int qRound(double d) {
     return d >= 0.0 ? int(d + 0.5) : int(d - 0.5);
 }
 
+// QT_SHIM_NODRAW=1 turns every draw call into a no-op: the "logic only" CPU baseline row of
+// SURVEY §8(d) (an upper bound on the reference's speed with a free rasteriser). Measurement only.
+static inline bool nodraw() {
+    static const bool v = getenv("QT_SHIM_NODRAW") != nullptr;
+    return v;
+}
+
 static inline uint32_t BYTE_MUL(uint32_t x, uint32_t a) {
     uint32_t t = (x & 0xff00ff) * a;
     t = (t + ((t >> 8) & 0xff00ff) + 0x800080) >> 8;
@@ -317,6 +324,8 @@ void QPainter::fillRect(const QRect &r, const QColor &c) {
 }
 
 void QPainter::fillRect(const QRectF &r0, const QColor &c) {
+    if (nodraw())
+        return;
     QImage *dev = d->dev;
     const Xform &m = d->cur.m;
     QRectF r(r0.x() + m.dx, r0.y() + m.dy, r0.width(), r0.height());
@@ -864,6 +873,8 @@ static void draw_rotated(QImage *dev, const QImage &img, const QRectF &r, const 
 }
 
 void QPainter::drawImage(const QRectF &target, const QImage &image) {
+    if (nodraw())
+        return;
     const Xform &m = d->cur.m;
     int io = int(d->cur.opacity * 256);
     static const bool trace = getenv("QT_SHIM_TRACE") != nullptr;
@@ -997,6 +1008,8 @@ static const EllipseRowSpan kCompassEasyRows[] = {{1, 52, 58},  {2, 50, 59},  {3
                                                   {13, 47, 62}, {14, 48, 61}, {15, 49, 60}, {16, 51, 59}, {17, 53, 57}};
 
 void QPainter::drawEllipse(const QRectF &rr) {
+    if (nodraw())
+        return;
     const Xform &m = d->cur.m;
     const double x = rr.x() * m.m11 + m.dx, y = rr.y() * m.m22 + m.dy, w = rr.width() * m.m11, h = rr.height() * m.m22;
     const int io = int(d->cur.opacity * 256);
@@ -1036,6 +1049,8 @@ static inline int fdot16_div(int x, int y) {
     return x * (1 << 16) / y;
 }
 void QPainter::drawLine(int ix1, int iy1, int ix2, int iy2) {
+    if (nodraw())
+        return;
     if (!d->cur.pen.on)
         return;
     QImage *dev = d->dev;
