@@ -999,7 +999,7 @@ static void ellipse_midpoint(const EllipseCtx &e) {
 //  * any other rect goes through Qt's generic path code (Bezier flattening + scan conversion + a
 //    cosmetic stroke of the outline). The only such call in scope is jumper easy mode's disc,
 //    whose rect is a constant of the 64x64 contract (visibility 12, compass_dim 3): its pixel
-//    rows were captured once from Qt 6.6.3 (tools/qt6_compass_mask.py) and are replayed here.
+//    rows were captured once from Qt 6.6.3 (tests/tools/qt6_compass_mask.py) and are replayed here.
 //    Anything else is reported, never approximated.
 struct EllipseRowSpan { int y, x1, x2; };
 static const double kCompassEasyRect[4] = {46.66666793823242, 1.3333333730697632, 16.0, 16.0};

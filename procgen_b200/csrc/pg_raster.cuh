@@ -729,7 +729,7 @@ PG_HD void ellipse_points(RotBlit &rb, int rx, int ry, int rw, int rh, bool pen,
 // QRasterPaintEngine::drawEllipse on a device rect (pen at most one pixel wide, same colour as the
 // brush, or no pen). Integer-aligned rects run drawEllipse_midpoint_i; the one non-aligned rect in
 // scope — jumper easy mode's compass disc, a constant of the 64x64 contract — replays the rows
-// captured from Qt 6.6.3 (tools/qt6_compass_mask.py). Returns false for anything else.
+// captured from Qt 6.6.3 (tests/tools/qt6_compass_mask.py). Returns false for anything else.
 template <class Frame>
 PG_HD bool make_ellipse_blit(Frame &f, Blit &b, int k, double x, double y, double w, double h, uint32_t argb_premultiplied, bool pen) {
     RotBlit *rbp = span_blit_begin(f, b, k, argb_premultiplied);

@@ -1,13 +1,13 @@
 """CPU rows of SURVEY §8(d) on this machine: the reference's game logic (compiled unmodified) with
 (ii) the restated raster and (i) a free rasteriser (QT_SHIM_NODRAW), sweeping num_threads and N.
-usage: python tools/cpu_reference_sweep.py [game] [mode]   -> JSON lines on stdout"""
+usage: python tests/tools/cpu_reference_sweep.py [game] [mode]   -> JSON lines on stdout"""
 import json
 import os
 import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 CHILD = r'''

@@ -1,13 +1,13 @@
 """Regenerates the pixel rows of jumper easy mode's compass disc from the real Qt 6 raster engine
 (the constant table in oracle/shim/qt_raster.cpp and procgen_b200/csrc/games/jumper.cuh).
-Needs the Qt 6 backed oracle (oracle/_ref/libenv_ref_qt6.so): python tools/qt6_compass_mask.py"""
+Needs the Qt 6 backed oracle (oracle/_ref/libenv_ref_qt6.so): python tests/tools/qt6_compass_mask.py"""
 import ctypes as C
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import qt6_support  # noqa: E402
 from oracle.ref_env import REF_LIB_QT6  # noqa: E402
 
