@@ -103,7 +103,7 @@ def cpu_reference_rate(game, mode, budget_s=15.0, envs_per_worker=64, workers=No
 
     from oracle.ref_env import RefVecEnv
 
-    cores = os.cpu_count() or 1
+    cores = host_cpu_info()["usable"]
     workers = cores if workers is None else workers
     n = envs_per_worker
     envs = [RefVecEnv(n, game, distribution_mode=mode, num_levels=0, start_level=0, rand_seed=w, num_threads=0)
@@ -166,7 +166,7 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": detail["cores"], "kind": "reference",
-                         "sample": detail["sample"] + " per bench step; reference game logic compiled unmodified, "
+                         "host": host_cpu_info(), "sample": detail["sample"] + " per bench step; reference game logic compiled unmodified, "
                                    "Qt raster restated on CPU (Qt itself is not installable here)"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -181,6 +181,77 @@ def workload_config(args):
             "parallelism": f"env-sharded x{args.gpus}, " + ("rgb gathered to rank 0 every step (NCCL)" if getattr(args, "gather", False)
                                                                else "no per-step collective"),
             "l2": "per-step working set (12 KiB obs + env state per env x num_envs) exceeds the 126 MB L2; no explicit flush"}
+
+
+def host_cpu_info():
+    """What the CPU arm can really use: affinity mask and cgroup quota next to os.cpu_count()."""
+    info = {"os_cpu_count": os.cpu_count()}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = None
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    info["cgroup_cpu_quota"] = quota
+    usable = info["affinity"] or info["os_cpu_count"] or 1
+    if quota:
+        usable = max(1, min(usable, int(quota + 0.5)))
+    info["usable"] = usable
+    return info
+
+
+def timed_rollout(env, actions, t0, K, barrier, gather=False, dist=None):
+    """K steps through the public API (env.act / env.observe), CUDA events on the launching stream."""
+    import torch
+
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    T = actions.shape[0]
+    barrier()
+    ev0.record()
+    for t in range(K):
+        env.act(actions[(t0 + t) % T])
+        rew, ob, first = env.observe()                           # aliases of HBM buffers; nothing to copy
+        if gather and dist is not None:
+            env.gather_observations(0)                           # the one collective of SURVEY §8e
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
+def reset_fraction(env, actions, t0, steps):
+    """Share of env-steps that ended an episode (observe() returned first=1), untimed pass."""
+    import torch
+
+    T = actions.shape[0]
+    acc = torch.zeros((), device=actions.device, dtype=torch.float64)
+    for t in range(steps):
+        env.act(actions[(t0 + t) % T])
+        rew, ob, first = env.observe()
+        acc += first.sum()
+    return float(acc.item()) / (steps * env.num)
+
+
+def max_over_ranks(x, dist, dev):
+    import torch
+
+    if dist is None:
+        return x
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def run_ours(args):
@@ -204,53 +275,53 @@ def run_ours(args):
     n = args.envs_per_gpu
     K, W = args.steps, args.warmup
 
-    env = ProcgenGym3Env(n, args.game, distribution_mode=args.mode, num_levels=0, start_level=0, rand_seed=0,
-                         shard=(rank, world) if world > 1 else None)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    actions = torch.randint(0, 15, (W + K, n), device=dev, dtype=torch.int32, generator=gen)
-    env.observe()
-    torch.cuda.synchronize()
-
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    env = ProcgenGym3Env(n, args.game, distribution_mode=args.mode, num_levels=0, start_level=0, rand_seed=0,
+                         shard=(rank, world) if world > 1 else None)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    T = 256
+    actions = torch.randint(0, 15, (T, n), device=dev, dtype=torch.int32, generator=gen)
+    if args.chunks:
+        env.set_launch_shape(chunks=args.chunks, serialize=False)   # profiling aid: fixed launch shape
+    env.observe()
+    torch.cuda.synchronize()
+
+    # ---- cold: right after the synchronised initial reset (every env at step 0 of its first episode)
     for t in range(W):
         env.act(actions[t])
         env.observe()
-    barrier()
+    cold_ms = max_over_ranks(timed_rollout(env, actions, W, K, barrier), dist, dev)
+    steps_done = W + K
 
+    # ---- desynchronise: a rollout long enough that episode boundaries (level generation) are spread
+    # over the steps the way they are in training; SURVEY §8(d) measures 1000 steps after 100 warm-up
+    t_d = time.perf_counter()
+    for t in range(args.desync_steps):
+        env.act(actions[(steps_done + t) % T])
+        env.observe()
+    torch.cuda.synchronize()
+    desync_s = time.perf_counter() - t_d
+    steps_done += args.desync_steps
+
+    # ---- steady state (the headline)
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
     time.sleep(0.15)
     launches0 = env.kernel_launches()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    ev0.record()
-    for t in range(K):
-        env._ac.copy_(actions[W + t], non_blocking=True)      # act(): action tensor -> library buffer (D2D)
-        kev[t][0].record()
-        env._lib.pgb200_act_device(env._h)                      # the step+render kernel
-        kev[t][1].record()
-        rew, ob, first = env.observe()                           # aliases of HBM buffers; nothing to copy
-        if args.gather and dist is not None:
-            gathered = env.gather_observations(0)                # the one collective of SURVEY §8e
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    elapsed_ms = max_over_ranks(timed_rollout(env, actions, steps_done, K, barrier, gather=args.gather, dist=dist), dist, dev)
     launches = env.kernel_launches() - launches0
     clocks = sampler.stop()
-    checksum = int(ob["rgb"].sum().item())
-    errors = env.errors()
-    if dist is not None:
-        tmax = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tmax.item())
+    steps_done += K
     value = n * world * K / (elapsed_ms / 1000.0)
+    value_cold = n * world * K / (cold_ms / 1000.0)
+    rfrac = reset_fraction(env, actions, steps_done, max(20, min(100, K)))
+    steps_done += max(20, min(100, K))
+    checksum = int(env.observe()[1]["rgb"].sum().item())
+    errors = env.errors()
 
     # ---- roofline pass: the same steps with every kernel launched back to back on one stream (one
     # launch per game covering all its envs) and CUDA events recorded around each launch on that
@@ -259,11 +330,11 @@ def run_ours(args):
     Kr = max(5, min(20, K))
     env.set_launch_shape(chunks=1, serialize=True)
     for t in range(3):
-        env.act(actions[t % (W + K)])
+        env.act(actions[t % T])
         env.observe()
     env.kernel_timing_begin(Kr * 64)
     for t in range(Kr):
-        env.act(actions[(W + t) % (W + K)])
+        env.act(actions[(W + t) % T])
         env.observe()
     ktimes = env.kernel_timing_end()
     env.set_launch_shape(chunks=0, serialize=False)
@@ -285,15 +356,42 @@ def run_ours(args):
             henv.act(host_actions[W + t])
             rew_h, ob_h, first_h = henv.observe()
         barrier()
-        el = time.perf_counter() - t0
-        if dist is not None:
-            tmax = torch.tensor([el], device=dev)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            el = float(tmax.item())
+        el = max_over_ranks(time.perf_counter() - t0, dist, dev)
+        d2h = (64 * 64 * 3 + 4 + 1 + 4 + 1 + 4) * n
         e2e = {"value": n * world * Ke / el, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n * world,
-               "d2h_bytes_per_step": (64 * 64 * 3 + 4 + 1 + 4 + 1 + 4) * n * world, "steps": Ke,
-               "api": "libenv_act + libenv_observe (host numpy buffers)", "timer": "host perf_counter around the calls"}
+               "d2h_bytes_per_step": d2h * world, "steps": Ke, "d2h_gbs_per_rank": d2h * Ke / el / 1e9,
+               "api": "libenv_act + libenv_observe (host numpy buffers)", "timer": "host perf_counter around the calls",
+               "note": "cold start (synchronised episodes); PCIe-bound, so level generation does not show"}
         henv.close()
+
+    # ---- BASELINE configs[4] riding along on multi-GPU runs: the 16-game list, 32 768 envs per GPU,
+    # without and with the per-step NCCL gather of every rank's rgb shard to rank 0
+    config5 = None
+    if args.config5 or (world > 1 and not args.no_config5 and "," not in args.game):
+        n5 = 32768
+        env5 = ProcgenGym3Env(n5, ALL16, distribution_mode="hard", num_levels=0, start_level=0, rand_seed=0,
+                              shard=(rank, world) if world > 1 else None)
+        act5 = torch.randint(0, 15, (64, n5), device=dev, dtype=torch.int32, generator=gen)
+        env5.observe()
+        K5 = max(10, min(30, K))
+        for t in range(args.config5_desync):
+            env5.act(act5[t % 64])
+            env5.observe()
+        ms_plain = max_over_ranks(timed_rollout(env5, act5, 0, K5, barrier), dist, dev)
+        config5 = {"workload": f"16-game list, {n5} envs/GPU x {world} GPUs = {n5 * world} envs, hard, after {args.config5_desync} "
+                               "desync steps", "steps": K5,
+                   "value": n5 * world * K5 / (ms_plain / 1000.0), "ms_per_step": ms_plain / K5, "unit": "env-steps/s"}
+        if dist is not None:
+            for t in range(2):
+                env5.act(act5[t])
+                env5.observe()
+                env5.gather_observations(0)
+            ms_g = max_over_ranks(timed_rollout(env5, act5, 0, K5, barrier, gather=True, dist=dist), dist, dev)
+            config5["with_gather"] = {"value": n5 * world * K5 / (ms_g / 1000.0), "ms_per_step": ms_g / K5,
+                                      "gather_bytes_per_step_into_rank0": (world - 1) * n5 * 64 * 64 * 3,
+                                      "how": env5.gather_how()}
+        config5["env_error_bits"] = env5.errors()
+        env5.close()
 
     if rank != 0:
         if dist is not None:
@@ -309,38 +407,56 @@ def run_ours(args):
     envs_per_launch = ktimes["env_steps"] / pairs
     algo_bytes_per_launch = ALGO_BYTES_PER_ENV_STEP * envs_per_launch
     achieved = algo_bytes_per_launch / (render_ms_avg / 1000.0) / 1e9 if render_ms_avg > 0 else 0.0
-    k_avg_ms = sum(kernel_ms) / len(kernel_ms)
+    step_ms = elapsed_ms / K
+    # DRAM bytes of ONE render_kernel launch from an `ncu --set full` capture taken at exactly this
+    # launch size (profiles/traffic_r02.json says which command produced it); null for any other shape
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    traffic_src = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            # ncu dram bytes of one render_kernel launch, scaled to this run's envs per launch
-            traffic = tj["render_kernel"]["dram_bytes_per_env"] * envs_per_launch
+            ent = tj.get(f"{args.game}:{args.mode}:{int(envs_per_launch)}")
+            if ent:
+                traffic = ent["dram_bytes_per_launch"]
+                traffic_src = ent.get("source")
         except Exception:
             traffic = None
     cpu = None
     if not args.no_cpu_baseline:
         rate, detail = cpu_reference_rate(args.game, args.mode, budget_s=args.cpu_budget)
-        cpu = {"value": rate, "unit": "env-steps/s", "cores": detail["cores"], "kind": "reference",
+        cpu = {"value": rate, "unit": "env-steps/s", "cores": detail["cores"], "kind": "reference", "host": host_cpu_info(),
                "sample": detail["sample"] + "; reference game logic compiled unmodified + Qt raster restated on CPU"}
     out = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+u8", "data": "synthetic", "config": workload_config(args),
+        "value_cold": value_cold, "ms_per_step_cold": cold_ms / K,
+        "steady_state": {"desync_steps": args.desync_steps, "desync_seconds": desync_s,
+                         "episode_end_fraction_per_step": rfrac,
+                         "note": "value = after the desync rollout (episode boundaries and level generation spread over "
+                                 "steps); value_cold = first K steps after the synchronised initial reset"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_kind": peak_kind, "kernel": f"render_kernel<{args.game}>",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                     "kernel": f"render_kernel<{args.game}>",
                      "kernel_ms_avg": render_ms_avg, "launches_timed": ktimes["launch_pairs"], "envs_per_launch": envs_per_launch,
                      "algorithmic_bytes_per_launch": algo_bytes_per_launch,
-                     "logic_kernel_ms_avg": logic_ms_avg, "step_ms_avg": k_avg_ms,
-                     "how": "CUDA events around each launch, launches serialised on one stream (separate pass of %d steps)" % Kr,
-                     "whole_step_achieved": ALGO_BYTES_PER_ENV_STEP * n / (k_avg_ms / 1000.0) / 1e9},
+                     "logic_kernel_ms_avg": logic_ms_avg, "step_ms_avg": step_ms,
+                     "how": "CUDA events around each launch, launches serialised on one stream (separate pass of %d steps, "
+                            "steady state)" % Kr,
+                     "whole_step_achieved": ALGO_BYTES_PER_ENV_STEP * n / (step_ms / 1000.0) / 1e9},
         "cpu_baseline": cpu, "obs_checksum": checksum, "env_error_bits": errors,
     }
+    if config5 is not None:
+        out["config5"] = config5
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+ALL16 = ("bigfish,bossfight,caveflyer,chaser,climber,coinrun,dodgeball,fruitbot,heist,jumper,leaper,maze,"
+         "miner,ninja,plunder,starpilot")
 
 
 def main():
@@ -356,12 +472,17 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--desync-steps", type=int, default=1500,
+                    help="untimed rollout before the steady-state measurement (episodes ~500-1000 steps)")
+    ap.add_argument("--chunks", type=int, default=0, help="profiling aid: env chunks per step (0 = library default)")
+    ap.add_argument("--config5", action="store_true", help="also measure BASELINE configs[4] (16-game list, 32768 envs/GPU)")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--config5-desync", type=int, default=300)
     ap.add_argument("--gather", action="store_true",
                     help="BASELINE configs[4] variant: NCCL-gather every step's rgb shard to rank 0 inside the timed region")
     args = ap.parse_args()
     if args.game == "all16":  # BASELINE configs[4]: env n plays game n % 16
-        args.game = ("bigfish,bossfight,caveflyer,chaser,climber,coinrun,dodgeball,fruitbot,heist,jumper,leaper,maze,"
-                     "miner,ninja,plunder,starpilot")
+        args.game = ALL16
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

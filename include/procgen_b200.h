@@ -184,6 +184,10 @@ LIBENV_API int pgb200_debug_cycles(libenv_env *handle, uint32_t *host_out);
  * max_ents entity records (128 B each, csrc/pg_state.cuh Entity) to host memory; returns n_ents. */
 LIBENV_API int pgb200_debug_read_env(libenv_env *handle, int env, void *hdr_out, void *ents_out, int max_ents);
 
+/* Introspection: shared memory of one render CTA (the per-game frame) and the number of render CTAs
+ * per SM the render kernel of `game` is compiled for. Returns -1 for an unknown game. */
+LIBENV_API int pgb200_frame_info(const char *game, int *frame_bytes, int *ctas_per_sm);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 LIBENV_API int64_t pgb200_kernel_launches(libenv_env *handle);
 

@@ -175,6 +175,8 @@ struct AtlasBuilder {
     std::vector<uint32_t> texels;                      // device atlas, u32 per texel
     std::map<std::string, SpriteDesc> sprite_cache;    // premultiplied sprites
     std::map<std::string, SpriteDesc> bg_cache;        // RGB32 backgrounds
+    std::vector<SpriteDesc> tile_sprites;              // rows of the pre-scaled tile table (one per distinct sprite)
+    std::map<uint32_t, int> slot_of_offset;
 
     explicit AtlasBuilder(const AssetPackReader &p) : pack(p) {}
 
@@ -206,6 +208,7 @@ struct AtlasBuilder {
 
     void build_game(int game_id, GameAssets &ga) {
         memset(&ga, 0, sizeof(ga));
+        for (auto &sl : ga.sprite_slot) sl = -1;
         GameAssetNames names = game_asset_names(game_id);
         add_reserved(names);
         for (auto &kv : names.by_type) {
@@ -220,6 +223,13 @@ struct AtlasBuilder {
                 SpriteDesc d = add(list[theme], true);
                 int idx = type + (int)theme * MAX_ASSETS;
                 ga.sprites[idx] = d;
+                auto it = slot_of_offset.find(d.off);
+                if (it == slot_of_offset.end()) {
+                    it = slot_of_offset.emplace(d.off, (int)tile_sprites.size()).first;
+                    tile_sprites.push_back(d);
+                }
+                if (it->second < 32767)
+                    ga.sprite_slot[idx] = (int16_t)it->second;
                 // basic-abstract-game.cpp:114: width() * 1.0 / height(), stored to a float
                 ga.aspect[idx] = (float)(d.w * 1.0 / d.h);
             }

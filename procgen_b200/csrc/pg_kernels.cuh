@@ -17,6 +17,7 @@ struct KParams {
     RotBlit *rot_scratch;       // [N][rot_stride] rotated-sprite records of frames too big for shared memory (may be null)
     const GameAssets *assets;   // table of the game this launch handles
     const uint32_t *atlas;
+    TileTable tiles;            // pre-scaled cell tiles of every sprite (texels == nullptr: disabled)
     // libenv-visible buffers (vecgame.cpp:212-268), one slot per env
     const int32_t *action;
     uint8_t *rgb;               // [N][64][64][3]
@@ -155,71 +156,57 @@ PG_HD void env_render_build(const KParams &p, int env, Frame &f, int tid, int nt
     Raster<G, Frame>::frame_build(c, f, tid, nthreads, ent_group);
 }
 
+// tile registration results -> arena space + staging jobs; tiles of tiled entities; deferred
+// rotated sprites. Independent of each other, so they share one barrier interval.
 template <class G, class Frame>
-PG_HD void env_render_tiles(const KParams &p, int env, Frame &f, int tid, int nthreads) {
-    if (f.n_jobs > 0) {
-        Ctx c = make_ctx(p, env);
+PG_HD void env_render_jobs(const KParams &p, int env, Frame &f, int tid, int nthreads) {
+    Ctx c = make_ctx(p, env);
+    Raster<G, Frame>::frame_tile_alloc(c, f, p.tiles, tid, nthreads);
+    if (f.n_jobs > 0)
         Raster<G, Frame>::frame_tiles(c, f, tid, nthreads);
-    }
-}
-
-template <class G, class Frame>
-PG_HD void env_render_rots(const KParams &p, int env, Frame &f, int tid, int nthreads) {
-    if (G::DEFER_ROTATED) {
-        Ctx c = make_ctx(p, env);
+    if (G::DEFER_ROTATED)
         Raster<G, Frame>::frame_rots(c, f, tid, nthreads);
-    }
+    if (tid == nthreads - 1)
+        Raster<G, Frame>::frame_append_overlays(f);
 }
 
 template <class G, class Frame>
 PG_HD void env_render_masks(const KParams &p, int env, Frame &f, int tid, int nthreads) {
+    Ctx c = make_ctx(p, env);
+    Raster<G, Frame>::frame_cells_finish(c, f, tid, nthreads);
     Raster<G, Frame>::frame_masks(f, tid, nthreads);
 }
 
-// R | G<<8 | B<<16 of a 0xAARRGGBB pixel: the byte order of the rgb888 observation (game.cpp:8-23)
-PG_HD uint32_t rgb24_of(uint32_t c) { return ((c >> 16) & 0xffu) | (c & 0xff00u) | ((c & 0xffu) << 16); }
-
-#if defined(__CUDACC__)
-// Device shading loop: thread t shades pixels t, t+T, ...; four neighbouring lanes hold one RGB
-// quad (12 bytes = 3 words), each of the first three lanes assembles one word from its own colour
-// and its right neighbour's (one shuffle) and stores it: every warp store instruction writes 96
-// contiguous bytes of the observation.
-template <class G, class Frame>
-__device__ __forceinline__ void env_render_pixels(const KParams &p, int env, const Frame &f, int tid, int nthreads) {
-    uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3));
-    const int j = tid & 3;
-    // nthreads is a multiple of RES_W: a thread's pixels all lie in one column
-    const int px = tid & (RES_W - 1);
-    typename Raster<G, Frame>::ColumnCtx cc;
-    Raster<G, Frame>::column_begin(f, px, cc);
-    for (int pix = tid; pix < RES_W * RES_H; pix += nthreads) {
-        const uint32_t c = rgb24_of(Raster<G, Frame>::shade_pixel(f, cc, px, pix >> 6, p.atlas));
-        const uint32_t cn = __shfl_down_sync(0xffffffffu, c, 1);
-        if (j != 3)
-            out[(pix >> 2) * 3 + j] = (c >> (8 * j)) | (cn << (24 - 8 * j));
-    }
+// Host debug harness twin of the bulk copies that stage the frame's tiles
+template <class Frame>
+PG_HD void env_stage_tiles_serial(const KParams &p, Frame &f) {
+    const int nj = f.n_tjobs < MAX_TILE_JOBS ? f.n_tjobs : MAX_TILE_JOBS;
+    for (int j = 0; j < nj; j++)
+        for (int w = 0; w < (int)f.tjob_words[j]; w++) f.arena[f.tjob_dst[j] + w] = p.tiles.texels[f.tjob_src[j] + w];
 }
-#endif
 
-// Shade 4 horizontally adjacent pixels and store them as 12 packed RGB bytes (3 aligned words):
-// bgr32_to_rgb888 (game.cpp:8-23) fused into the shader.
+// Shade rows py0, py0 + row_step, ... of the quad column starting at pixel px0 into `out`
+// (packed RGB, 48 words per row). Device: one thread; `out` is the frame's shared-memory copy.
 template <class G, class Frame>
-PG_HD void env_render_quad(const KParams &p, int env, const Frame &f, int quad) {
-    const int py = quad >> 4;
-    const int px0 = (quad & 15) << 2;
-    uint32_t c0 = Raster<G, Frame>::shade_pixel(f, px0 + 0, py, p.atlas);
-    uint32_t c1 = Raster<G, Frame>::shade_pixel(f, px0 + 1, py, p.atlas);
-    uint32_t c2 = Raster<G, Frame>::shade_pixel(f, px0 + 2, py, p.atlas);
-    uint32_t c3 = Raster<G, Frame>::shade_pixel(f, px0 + 3, py, p.atlas);
-    // 0xAARRGGBB -> bytes R,G,B
-    uint32_t r0 = (c0 >> 16) & 0xff, g0 = (c0 >> 8) & 0xff, b0 = c0 & 0xff;
-    uint32_t r1 = (c1 >> 16) & 0xff, g1 = (c1 >> 8) & 0xff, b1 = c1 & 0xff;
-    uint32_t r2 = (c2 >> 16) & 0xff, g2 = (c2 >> 8) & 0xff, b2 = c2 & 0xff;
-    uint32_t r3 = (c3 >> 16) & 0xff, g3 = (c3 >> 8) & 0xff, b3 = c3 & 0xff;
-    uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3)) + quad * 3;
-    out[0] = r0 | (g0 << 8) | (b0 << 16) | (r1 << 24);
-    out[1] = g1 | (b1 << 8) | (r2 << 16) | (g2 << 24);
-    out[2] = b2 | (r3 << 8) | (g3 << 16) | (b3 << 24);
+PG_HD void env_render_quad_column(const KParams &p, const Frame &f, int px0, int py0, int row_step, uint32_t *out) {
+    typename Raster<G, Frame>::QuadCtx q;
+    Raster<G, Frame>::quad_begin(f, px0, q);
+    for (int py = py0; py < RES_H; py += row_step)
+        Raster<G, Frame>::shade_quad(f, q, px0, py, p.atlas, out + py * (RES_W * 3 / 4) + (px0 >> 2) * 3);
+}
+
+// Fill one tile of the global table (TileTable): tile (slot, tw, th) = the texels an un-clipped
+// drawImage of the sprite at snapped size tw x th samples, by the general path's own arithmetic.
+PG_HD void tile_table_fill(const SpriteDesc *sprites, const uint32_t *index, uint32_t *texels, const uint32_t *atlas, int slot, int tw, int th, int tid,
+                           int nthreads) {
+    Blit b;
+    make_image_blit(b, 0.0, 0.0, (double)tw, (double)th, sprites[slot], false, 256, true);
+    uint32_t *dst = texels + index[(slot * MAX_TILE_DIM + (tw - 1)) * MAX_TILE_DIM + (th - 1)];
+    const int words = tile_words(tw, th);
+    for (int i = tid; i < words; i += nthreads) {
+        const int dy = i / tw, dx = i - dy * tw;
+        dst[i] = dy < th ? tile_texel(b, atlas, dx, dy) : 0u;
+    }
 }
 
 // Frame sizing per game: visible window (cells per side) and entity capacity.

@@ -64,7 +64,6 @@ static inline void pg_fatal(const char *fmt, ...) {
 constexpr int kLogicThreads = 32 * PG_LOGIC_WARPS;  // one warp = one env; few warps per CTA so a finished
 constexpr int kLogicEnvsPerBlock = PG_LOGIC_WARPS;  // env frees its slot without waiting on many siblings
 constexpr int kRenderThreads = 128;
-constexpr int kQuads = RES_W * RES_H / 4;
 
 #ifndef PG_HOSTSIM
 // Persistent: the grid is sized to fill the machine once and every warp pulls env indices from a
@@ -96,24 +95,66 @@ __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kern
 #ifndef PG_RENDER_CTAS_PER_SM
 #define PG_RENDER_CTAS_PER_SM 0  // 0 = as many as registers / the frame allow
 #endif
-// Resident CTAs per SM the render kernel is compiled for. The shader is issue-bound and gains from
-// occupancy (measured: +24 % on coinrun going from 6 to 8 CTAs/SM = 64 registers), but a frame
-// with hundreds of blits does not fit 8 times into shared memory, and there the register cap only
-// costs spills.
+// Resident CTAs per SM the render kernel is compiled for: as many as the frame (shared memory)
+// allows; the register cap follows (65536 / (128 * CTAs)).
 template <class G>
 struct RenderTune {
     static constexpr size_t kFrameBytes = sizeof(typename FrameFor<G>::type);
 #ifdef PG_RENDER_MIN_BLOCKS
     static constexpr int kMinBlocks = PG_RENDER_MIN_BLOCKS;
 #else
-    static constexpr int kMinBlocks = kFrameBytes <= 27 * 1024 ? 8 : (kFrameBytes <= 36 * 1024 ? 6 : 1);
+    // 227 KiB usable per SM, 1 KiB reserved per resident CTA
+    static constexpr int kFit = (int)((227 * 1024) / (kFrameBytes + 1024 + 16));
+    static constexpr int kMinBlocks = kFit >= 8 ? 8 : (kFit >= 1 ? kFit : 1);
 #endif
 };
 
+// ---- async-proxy plumbing (PTX): mbarrier + bulk copies (the TMA engine's 1-D mode; SASS UBLKCP)
+__device__ __forceinline__ uint32_t pg_smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void pg_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pg_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pg_mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pg_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {  // try_wait suspends the thread in hardware for a while before it returns false
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(pg_smem_addr(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// global -> shared, completion counted on the mbarrier; 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void pg_bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pg_smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(pg_smem_addr(bar))
+                 : "memory");
+}
+// shared -> global; returns once the engine has read the source (the CTA may then exit / reuse it)
+__device__ __forceinline__ void pg_bulk_store_and_wait(void *dst_gmem, const void *src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(pg_smem_addr(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// One CTA renders one env's frame:
+//   begin / build / jobs   the blit lists, the cell map and the list of pre-scaled tiles the frame needs
+//   stage                  warp 0 arms the mbarrier and queues one bulk copy per tile (global table -> shared)
+//   masks                  meanwhile: cell codes, row / column masks of the entity blits
+//   shade                  thread = 4 pixel columns x 8 rows, top-down walk per pixel, packed RGB into shared
+//   store                  one bulk copy of the 12 KiB frame to the observation buffer
 template <class G>
 __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) render_kernel(KParams p) {
     using Frame = typename FrameFor<G>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Frame &f = *reinterpret_cast<Frame *>(smem_raw);
     const int env = p.env_first + (int)blockIdx.x * p.env_step;
     const int tid = (int)threadIdx.x;
@@ -129,27 +170,40 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
 #else
 #define PG_RENDER_PHASE(id) do { } while (0)
 #endif
+    if (tid == 0)
+        pg_mbar_init(&f.mbar, 1);
     env_render_begin<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
     PG_RENDER_PHASE(8);
     env_render_build<G, Frame>(p, env, f, tid, kRenderThreads, 32);
     __syncthreads();
+    env_render_jobs<G, Frame>(p, env, f, tid, kRenderThreads);
+    __syncthreads();
     PG_RENDER_PHASE(9);
-    if (f.n_jobs > 0) {  // block-uniform
-        env_render_tiles<G, Frame>(p, env, f, tid, kRenderThreads);
-        __syncthreads();
-    }
-    if (G::DEFER_ROTATED) {  // compile-time, per game
-        env_render_rots<G, Frame>(p, env, f, tid, kRenderThreads);
-        __syncthreads();
+    if (G::DRAWS_GRID && tid < 32) {
+        const int nj = f.n_tjobs < MAX_TILE_JOBS ? f.n_tjobs : MAX_TILE_JOBS;
+        if (tid == 0) {
+            unsigned bytes = 0;
+            for (int j = 0; j < nj; j++) bytes += 4u * f.tjob_words[j];
+            pg_mbar_arrive_expect_tx(&f.mbar, bytes);
+        }
+        __syncwarp();
+        for (int j = tid; j < nj; j += 32) pg_bulk_load(f.arena + f.tjob_dst[j], p.tiles.texels + f.tjob_src[j], 4u * f.tjob_words[j], &f.mbar);
     }
     env_render_masks<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
     PG_RENDER_PHASE(10);
-    env_render_pixels<G, Frame>(p, env, f, tid, kRenderThreads);
+    if (G::DRAWS_GRID)
+        pg_mbar_wait(&f.mbar, 0);
+    env_render_quad_column<G, Frame>(p, f, (tid & 15) << 2, tid >> 4, kRenderThreads >> 4, f.out);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of f.out -> visible to the bulk copy
+    __syncthreads();
     PG_RENDER_PHASE(11);
+    if (tid == 0)
+        pg_bulk_store_and_wait(p.rgb + (size_t)env * (RES_W * RES_H * 3), f.out, RES_W * RES_H * 3);
 #undef PG_RENDER_PHASE
 }
+
 #endif
 
 #ifndef PG_HOSTSIM
@@ -165,6 +219,18 @@ __global__ void camera_kernel(KParams p) {
     }
 }
 #endif
+
+// the render kernel's phases as plain loops (host debug harness; also documents the phase order)
+template <class G, class Frame>
+void render_env_serial(const KParams &p, int env, Frame &f) {
+    env_render_begin<G, Frame>(p, env, f, 0, 1);
+    env_render_build<G, Frame>(p, env, f, 0, 1, 1);
+    env_render_jobs<G, Frame>(p, env, f, 0, 1);
+    env_stage_tiles_serial<Frame>(p, f);
+    env_render_masks<G, Frame>(p, env, f, 0, 1);
+    uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3));
+    for (int qx = 0; qx < RES_W / 4; qx++) env_render_quad_column<G, Frame>(p, f, qx * 4, 0, 1, out);
+}
 
 struct LaunchCtx {
 #ifndef PG_HOSTSIM
@@ -233,10 +299,7 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
             env_init_logic<G, Frame>(p, env);
         else
             env_step_logic<G, Frame>(p, env);
-        env_render_begin<G, Frame>(p, env, *f, 0, 1);
-        env_render_build<G, Frame>(p, env, *f, 0, 1, 1);
-        env_render_masks<G, Frame>(p, env, *f, 0, 1);
-        for (int quad = 0; quad < kQuads; quad++) env_render_quad<G, Frame>(p, env, *f, quad);
+        render_env_serial<G, Frame>(p, env, *f);
     }
     (*lc.launch_counter) += 2;
 #endif
@@ -259,10 +322,7 @@ void launch_observe_only(const KParams &p, const LaunchCtx &lc) {
         Ctx c = make_ctx(p, env);
         Raster<G, Frame>::prepare_camera(c);
         write_step_outputs(p, env, *c.h);
-        env_render_begin<G, Frame>(p, env, *f, 0, 1);
-        env_render_build<G, Frame>(p, env, *f, 0, 1, 1);
-        env_render_masks<G, Frame>(p, env, *f, 0, 1);
-        for (int quad = 0; quad < kQuads; quad++) env_render_quad<G, Frame>(p, env, *f, quad);
+        render_env_serial<G, Frame>(p, env, *f);
     }
 #endif
     (*lc.launch_counter) += 2;
@@ -273,6 +333,8 @@ struct GameVTable {
     int id;
     int ent_cap, grid_cap, scratch_words;
     int rot_records;  // rotated-sprite records kept in global memory per env (0 = the frame holds them)
+    int frame_bytes;  // shared memory of one render CTA
+    int render_ctas_per_sm;  // residency the render kernel is compiled for
     void (*init)(const KParams &, const LaunchCtx &);
     void (*step)(const KParams &, const LaunchCtx &);
     void (*observe_only)(const KParams &, const LaunchCtx &);
@@ -281,6 +343,12 @@ struct GameVTable {
 template <class G>
 GameVTable make_vtable(int id) {
     return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, FrameFor<G>::type::kRotInGlobal ? G::MAX_ROT_BLITS : 0,
+                      (int)sizeof(typename FrameFor<G>::type),
+#ifndef PG_HOSTSIM
+                      RenderTune<G>::kMinBlocks,
+#else
+                      0,
+#endif
                       &launch_env_kernel<G, true>, &launch_env_kernel<G, false>, &launch_observe_only<G>};
 }
 

@@ -65,6 +65,36 @@ struct Camera {
     float unit, view_dim, x_off, y_off;
 };
 
+// ---- pre-scaled cell tiles (global table, built once per VecEnv by tile_table_fill)
+// With Qt's integer snapping an un-clipped, un-rotated, un-mirrored drawImage of integer target
+// size (tw, th) samples the same tw x th texels of its sprite wherever it lands (make_image_blit:
+// the 16.16 start `ceil(0.5 * sx * 65536) - 1` and the step do not depend on the position). Grid
+// cells are exactly that, hundreds per frame, in one or two sizes: so every sprite is resampled
+// once for every target size up to MAX_TILE_DIM^2 — by make_image_blit itself, so the texels are
+// the ones the general path would fetch — and a frame stages the few tiles it needs in shared
+// memory with bulk async copies (cp.async.bulk + mbarrier) while its entity blits are built.
+constexpr int MAX_TILE_DIM = 12;
+constexpr int TILE_VARIANTS = MAX_TILE_DIM * MAX_TILE_DIM;
+struct TileTable {
+    const uint32_t *texels;   // tile (slot, tw, th): tw*th texels, row stride tw, padded to a multiple of 4 texels
+    const uint32_t *index;    // [slot][tw-1][th-1] -> texel offset of the tile (multiple of 4)
+    const SpriteDesc *sprites;  // [slot]
+    int32_t n_slots;
+};
+PG_HD int tile_words(int tw, int th) { return (tw * th + 3) & ~3; }
+
+constexpr int CELL_KEY_TYPES = 128;              // grid object ids that can use a tile (others take the general path)
+constexpr int CELL_KEYS = CELL_KEY_TYPES * 4;    // x (tw - W0, th - H0) in {0,1}^2
+constexpr uint16_t CELL_GENERAL = 0x8000u;       // cellmap code: 0 none | 1 + texel offset of its tile in the arena | CELL_GENERAL | blit index
+constexpr int MAX_TILE_JOBS = 96;
+
+// colinfo / rowinfo word of a pixel column / row (cells of the visible grid window)
+constexpr uint32_t CI_BASE_MASK = 0x3ffu;        // column: ci * ny; row: cj
+constexpr uint32_t CI_VALID = 1u << 10;          // some cell column / row covers the pixel
+constexpr int CI_D_SHIFT = 11;                   // 5 bits: px - col_p1 (py - row_p1)
+constexpr int CI_TW_SHIFT = 16;                  // 5 bits, column only: row stride of its tiles (0: not tile-eligible)
+constexpr uint32_t CI_MULTI = 1u << 21;          // more than one cell column / row covers the pixel
+
 template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
 struct FrameT {
     static constexpr int kMaxCells1D = MAX_CELLS_1D;
@@ -73,26 +103,45 @@ struct FrameT {
     // records (208 B each) and fit only 2-3 times per SM; above 32 records they live in the env's
     // slice of a global scratch array instead (L1/L2 resident while the CTA works on the frame).
     static constexpr bool kRotInGlobal = MAX_ROT_BLITS > 32;
+    // ---- 16-byte aligned blocks first (bulk-copy targets / sources)
+    // packed RGB frame, assembled here and written out with one bulk store
+    alignas(16) uint32_t out[RES_W * RES_H * 3 / 4];
+    // tiles (texels, growing up from word 0) and general cell blits (32 B each, growing down from the end)
+    static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 8;
+    alignas(16) uint32_t arena[kArenaWords];
+    alignas(8) unsigned long long mbar;   // tile staging barrier
     int32_t n_rot;
     RotBlit *rot;
     RotBlit rot_local[kRotInGlobal ? 1 : kMaxRot];
-    static constexpr int kMaxEntBlits = MAX_ENT_BLITS;   // VISIBLE entity blits (after culling)
+    // `ents` = VISIBLE entity blits (after culling) in draw order, then the overlay blits (drawn last)
+    static constexpr int kMaxEntBlits = MAX_ENT_BLITS - MAX_OVERLAY_BLITS;
     Camera cam;
     int32_t low_x, low_y, nx, ny;   // visible grid window: cells [low_x, low_x+nx) x [low_y, low_y+ny)
     int32_t n_bg, n_ent, n_ent_below, n_overlay;  // n_ent_below = entities with render_z == -1
     int32_t snap;
-    int32_t pad;
+    int32_t pad;                    // 1: the background is one opaque image covering the device (bgrow[] valid)
+    int32_t tile_w0, tile_h0;       // smaller of the two snapped cell sizes of this frame
+    int32_t n_gen;                  // general cell blits in use
+    int32_t tile_top;               // arena words used by tiles
+    int32_t n_tjobs;
     // geometry shared by all cells of a column / row (the cell rect is separable)
     double col_x[MAX_CELLS_1D];     // QRectF.x of column i
     double row_y[MAX_CELLS_1D];     // QRectF.y of row j
     double cell_w;                  // QRectF.width == height
     uint8_t col_p1[MAX_CELLS_1D], col_p2[MAX_CELLS_1D];  // device pixel span [p1,p2) of column i
     uint8_t row_p1[MAX_CELLS_1D], row_p2[MAX_CELLS_1D];
+    uint8_t col_tw[MAX_CELLS_1D], row_th[MAX_CELLS_1D];  // snapped size if the column / row can use tiles, else 0
     static constexpr int kEntWords = (MAX_ENT_BLITS + 63) / 64;
     uint64_t ent_rowmask[RES_H][kEntWords];  // bit i: visible entity blit i touches this pixel row
     uint64_t ent_colmask[RES_W][kEntWords];  //        ... this pixel column
     uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
     uint8_t row_lo[RES_H], row_hi[RES_H];
+    uint32_t colinfo[RES_W], rowinfo[RES_H];  // CI_* words
+    uint32_t bgrow[RES_H];                    // pad == 1: atlas offset of the background row sampled by pixel row py
+    uint16_t cellmap[MAX_CELLS_1D * MAX_CELLS_1D];  // [ci * ny + cj], x outer / y inner = draw order
+    uint16_t tilekey[MAX_CELLS_1D > 1 ? CELL_KEYS : 4];  // per (type, size variant): 0 unused | 1 wanted | 2 + arena texel offset | 0xffff unavailable
+    uint32_t tjob_src[MAX_TILE_JOBS];         // tile copies to stage: texel offset in the table,
+    uint16_t tjob_dst[MAX_TILE_JOBS], tjob_words[MAX_TILE_JOBS];  // arena word offset, words
     // tiled entities only reserve their blit slots while the list is built; the tiles themselves
     // are filled in by all threads afterwards (frame_tiles)
     static constexpr int kMaxTileJobs = 64;
@@ -101,7 +150,9 @@ struct FrameT {
     Blit bg[MAX_BG_BLITS];
     Blit overlay[MAX_OVERLAY_BLITS];
     Blit ents[MAX_ENT_BLITS];
-    Blit cells[MAX_CELLS_1D * MAX_CELLS_1D];  // [ci * ny + cj], x outer / y inner = draw order
+
+    PG_HD Blit *gen_blit(int k) { return reinterpret_cast<Blit *>(arena + kArenaWords) - 1 - k; }
+    PG_HD const Blit *gen_blit(int k) const { return reinterpret_cast<const Blit *>(arena + kArenaWords) - 1 - k; }
 };
 
 // ---- rule S: un-rotated scaled image (qt_scale_image_32bit)
@@ -593,44 +644,46 @@ PG_HD void make_solid_blit(Blit &b, double x, double y, double w, double h, uint
 }
 
 // ---- rules B + O
-PG_HD uint32_t blend_px(uint32_t dst, uint32_t src, int int_opacity) {
-    if (int_opacity == 256) {
-        if (src >= 0xff000000u)
-            return src;
-        if (src != 0)
-            return src + pg_byte_mul(dst, (~src) >> 24);
-        return dst;
-    }
-    if (src != 0) {
-        uint32_t s = pg_byte_mul(src, (uint32_t)((int_opacity * 255) >> 8));
+// One layer of the composition = the premultiplied source value a blit contributes at a pixel
+// (0: nothing), with the painter opacity already applied; layer_over is Qt's src-over.
+//   opaque (alpha 255): replaces what is below — the shader's top-down walk stops there
+//   opacity != 256:     s = BYTE_MUL(src, (io*255)>>8) has alpha <= 254, so it never looks opaque
+PG_HD uint32_t layer_over(uint32_t dst, uint32_t s) {
+    if (s >= 0xff000000u)
+        return s;
+    if (s != 0)
         return s + pg_byte_mul(dst, (~s) >> 24);
-    }
     return dst;
+}
+PG_HD uint32_t layer_of(uint32_t src, int int_opacity) {
+    if (int_opacity == 256 || src == 0)
+        return src;
+    return pg_byte_mul(src, (uint32_t)((int_opacity * 255) >> 8));
 }
 
 #if defined(PG_APPLY_NOINLINE) && defined(__CUDACC__)
-__host__ __device__ __noinline__ uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uint32_t *atlas, const RotBlit *rots) {
+__host__ __device__ __noinline__ uint32_t blit_texel(const Blit &b, int px, int py, const uint32_t *atlas, const RotBlit *rots) {
 #else
-PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uint32_t *atlas, const RotBlit *rots) {
+PG_HD uint32_t blit_texel(const Blit &b, int px, int py, const uint32_t *atlas, const RotBlit *rots) {
 #endif
     const uint32_t box = *reinterpret_cast<const uint32_t *>(&b);  // x1 | y1<<8 | w<<16 | h<<24
     const uint32_t dx = (uint32_t)px - (box & 0xffu);
     const uint32_t dy = (uint32_t)py - ((box >> 8) & 0xffu);
     if (dx >= ((box >> 16) & 0xffu) || dy >= (box >> 24))
-        return dst;
+        return 0;
     if (b.kind == BLIT_SOLID)
         return b.src;
     if (b.kind == BLIT_SPANS) {  // one solid-colour span per row (ellipse / cosmetic line), src-over
         const RotBlit &rb = rots[b.ix];
         if (px < (int)rb.x1[py] || px >= (int)rb.x2[py])
-            return dst;
-        return blend_px(dst, b.src, 256);
+            return 0;
+        return b.src;
     }
     if (b.kind == BLIT_ROTATED) {
         const RotBlit &rb = rots[b.ix];
         const int xs = rb.x1[py];
         if (px < xs || px >= (int)rb.x2[py])
-            return dst;
+            return 0;
         long long tu, tv;
         if (rb.absolute) {
             tu = ((long long)px * rb.dudx + (long long)py * rb.dudy + rb.u0) >> 16;
@@ -650,14 +703,26 @@ PG_HD uint32_t apply_blit(const Blit &b, int px, int py, uint32_t dst, const uin
         if (tv > (long long)b.sh - 1) tv = (long long)b.sh - 1;
         if (b.mirror)
             tu = b.sw - 1 - tu;
-        return blend_px(dst, atlas[b.src + (uint32_t)tv * b.sw + (uint32_t)tu], b.opacity);
+        return layer_of(atlas[b.src + (uint32_t)tv * b.sw + (uint32_t)tu], b.opacity);
     }
+    if (b.kind != BLIT_IMAGE)
+        return 0;
     uint32_t sx = (b.basex + (uint32_t)b.ix * dx) >> 16;
     uint32_t sy = (b.srcy + (uint32_t)b.iy * dy) >> 16;
     if (b.mirror)
         sx = b.sw - 1 - sx;
-    uint32_t texel = atlas[b.src + sy * b.sw + sx];
-    return blend_px(dst, texel, b.opacity);
+    return layer_of(atlas[b.src + sy * b.sw + sx], b.opacity);
+}
+
+// Tile (sprite, tw, th) of the global table: what an un-clipped, un-mirrored, opaque-painter
+// drawImage of snapped size tw x th fetches, pixel by pixel. Texels the edge guards of
+// make_image_blit drop are 0 (= nothing drawn).
+PG_HD uint32_t tile_texel(const Blit &b, const uint32_t *atlas, int dx, int dy) {
+    if (b.kind != BLIT_IMAGE || dx >= (int)b.w || dy >= (int)b.h)
+        return 0;
+    const uint32_t sx = (b.basex + (uint32_t)b.ix * (uint32_t)dx) >> 16;
+    const uint32_t sy = (b.srcy + (uint32_t)b.iy * (uint32_t)dy) >> 16;
+    return atlas[b.src + sy * b.sw + sx];
 }
 
 // ---- rules E / L: QPainter::drawEllipse and drawLine as the raster engine runs them for the
@@ -1063,11 +1128,16 @@ struct Raster {
         ny = high_y - low_y + 1;
     }
 
-    static PG_HD void span_of(double t, double tw, bool snap, int limit, uint8_t &p1, uint8_t &p2) {
+    // device pixel span [p1, p2) of a cell column / row, and (tile_size) its snapped size when the
+    // column's cells are un-clipped on the near side so that pre-scaled tiles apply (else 0)
+    static PG_HD void span_of(double t, double tw, bool snap, int limit, uint8_t &p1, uint8_t &p2, uint8_t &tile_size) {
+        tile_size = 0;
         if (snap) {
             double x = pg_qround(t);
             tw = pg_qround(t + tw - x);
             t = x;
+            if (x >= 0 && tw >= 1 && tw <= MAX_TILE_DIM)
+                tile_size = (uint8_t)(int)tw;
         }
         int a = pg_qround(t), b2 = pg_qround(t + tw);
         if (a < 0) a = 0;
@@ -1093,6 +1163,10 @@ struct Raster {
         bool overflow = false;
         if (nx > Frame::kMaxCells1D) { nx = Frame::kMaxCells1D; overflow = true; }
         if (ny > Frame::kMaxCells1D) { ny = Frame::kMaxCells1D; overflow = true; }
+        // the two snapped sizes a cell can have: floor(w) and floor(w) + 1 (w = QRectF width of a cell)
+        double cw[4];
+        screen_rect(cam, 0.f, 1.f, 1, 1, RENDER_EPS, cw);
+        const int w0 = (int)pg_dfloor(cw[2]);
         if (tid == 0) {
             f.cam = cam;
             f.snap = snap ? 1 : 0;
@@ -1106,6 +1180,10 @@ struct Raster {
             f.n_ent_below = 0;
             f.n_rot = 0;
             f.n_jobs = 0;
+            f.n_gen = 0;
+            f.tile_top = 0;
+            f.n_tjobs = 0;
+            f.tile_w0 = f.tile_h0 = w0;
             f.rot = Frame::kRotInGlobal ? reinterpret_cast<RotBlit *>(c.rot_scratch_raw) : f.rot_local;
             if (Frame::kRotInGlobal && c.rot_scratch_raw == nullptr) {
                 h.err |= ERR_SCRATCH_OVERFLOW;
@@ -1140,6 +1218,10 @@ struct Raster {
             }
             G::make_overlay_blits(c, f);  // game overlays are appended after the velocity squares
         }
+        if (G::DRAWS_GRID) {
+            uint32_t *keys = reinterpret_cast<uint32_t *>(f.tilekey);
+            for (int i = tid; i < CELL_KEYS / 2; i += nthreads) keys[i] = 0;
+        }
         // columns by threads 0.., rows by threads from the top end so they land on other lanes
         for (int i = tid; i < nx; i += nthreads) {
             double r[4];
@@ -1147,18 +1229,23 @@ struct Raster {
             f.col_x[i] = r[0];
             if (i == 0)
                 f.cell_w = r[2];
-            span_of(r[0], r[2], snap, RES_W, f.col_p1[i], f.col_p2[i]);
+            uint8_t ts;
+            span_of(r[0], r[2], snap, RES_W, f.col_p1[i], f.col_p2[i], ts);
+            f.col_tw[i] = (ts == w0 || ts == w0 + 1) ? ts : 0;
         }
         for (int jj = tid; jj < ny; jj += nthreads) {
             int j = ny - 1 - jj;
             double r[4];
             screen_rect(cam, (float)low_x, (float)(low_y + j + 1), 1, 1, RENDER_EPS, r);
             f.row_y[j] = r[1];
-            span_of(r[1], r[3], snap, RES_H, f.row_p1[j], f.row_p2[j]);
+            uint8_t ts;
+            span_of(r[1], r[3], snap, RES_H, f.row_p1[j], f.row_p2[j], ts);
+            f.row_th[j] = (ts == w0 || ts == w0 + 1) ? ts : 0;
         }
     }
 
-    static PG_HD void cell_lookup(const uint8_t *p1, const uint8_t *p2, int n, int px, uint8_t &lo, uint8_t &hi) {
+    // cell columns (rows) covering pixel column (row) p -> lo / hi and the packed CI_* word
+    static PG_HD uint32_t cell_lookup(const uint8_t *p1, const uint8_t *p2, const uint8_t *tsize, int n, int base_mul, int px, uint8_t &lo, uint8_t &hi) {
         int l = 255, hgh = 0;
         for (int i = 0; i < n; i++) {
             if (px >= p1[i] && px < p2[i]) {
@@ -1173,6 +1260,12 @@ struct Raster {
         }
         lo = (uint8_t)l;
         hi = (uint8_t)hgh;
+        if (l == 255)
+            return 0;
+        uint32_t w = (uint32_t)(hgh * base_mul) | CI_VALID | ((uint32_t)((px - p1[hgh]) & 31) << CI_D_SHIFT) | ((uint32_t)tsize[hgh] << CI_TW_SHIFT);
+        if (l != hgh)
+            w |= CI_MULTI;
+        return w;
     }
 
     // tile_image (basic-abstract-game.cpp:840-869): number of tiles an entity's sprite is repeated
@@ -1422,9 +1515,9 @@ struct Raster {
         }
     }
 
-    // ---- phase C. Few entities: warp 0 builds the entity list while the other warps build the
-    // cells and the pixel -> cell lookups. Many entities (bullet-heavy frames, tiled walls): the
-    // whole CTA builds the list, then the cells.
+    // ---- phase C. Few entities: warp 0 builds the entity list while the other warps classify the
+    // cells and build the pixel -> cell lookups. Many entities (bullet-heavy frames, tiled walls):
+    // the whole CTA builds the list, then the cells.
     static PG_HD void frame_build(Ctx &c, Frame &f, int tid, int nthreads, int /*unused*/) {
         int wtid = tid, wn = nthreads;
         if (nthreads > 32 && c.h->n_ents <= 32) {
@@ -1437,27 +1530,138 @@ struct Raster {
         } else {
             build_entity_blits(c, f, tid, nthreads);
         }
+        if (f.pad == 1) {
+            const Blit &b = f.bg[0];
+            for (int py = wtid; py < RES_H; py += wn) f.bgrow[py] = b.src + ((b.srcy + (uint32_t)b.iy * (uint32_t)py) >> 16) * b.sw;
+        }
         if (!G::DRAWS_GRID)
             return;
         for (int px = wtid; px < RES_W + RES_H; px += wn) {
             if (px < RES_W)
-                cell_lookup(f.col_p1, f.col_p2, f.nx, px, f.col_lo[px], f.col_hi[px]);
+                f.colinfo[px] = cell_lookup(f.col_p1, f.col_p2, f.col_tw, f.nx, f.ny, px, f.col_lo[px], f.col_hi[px]);
             else
-                cell_lookup(f.row_p1, f.row_p2, f.ny, px - RES_W, f.row_lo[px - RES_W], f.row_hi[px - RES_W]);
+                f.rowinfo[px - RES_W] = cell_lookup(f.row_p1, f.row_p2, f.row_th, f.ny, 1, px - RES_W, f.row_lo[px - RES_W], f.row_hi[px - RES_W]);
         }
+        // Cells, pass A (draw_grid_obj / draw_image for a grid cell, basic-abstract-game.cpp:877-919,
+        // 940-950): a cell whose sprite can come from the pre-scaled tile table only registers the
+        // tile it needs; everything else (near-side clipped columns and rows, solid-colour cells,
+        // adjusted rects, no snapping) becomes a general blit right away.
         const int ncells = f.nx * f.ny;
+        const bool mono = c.h->options.use_monochrome_assets != 0;
         for (int k = wtid; k < ncells; k += wn) {
             int ci = k / f.ny, cj = k - ci * f.ny;
-            Blit &b = f.cells[k];
-            blit_clear(b);
+            f.cellmap[k] = 0;
             if (f.col_p1[ci] >= f.col_p2[ci] || f.row_p1[cj] >= f.row_p2[cj])
                 continue;  // entirely off screen
             int type = E::get_obj(c, f.low_x + ci, f.low_y + cj);
             if (type == INVALID_OBJ)
                 continue;
-            int theme = G::theme_for_grid_obj(c, type);
+            const int theme = G::theme_for_grid_obj(c, type);
+            const int tw = f.col_tw[ci], th = f.row_th[cj];
+            if (tw && th && !mono && type >= 0 && type < CELL_KEY_TYPES && theme >= 0 && theme < MAX_IMAGE_THEMES) {
+                const int img_type = G::image_for_type(c, type);
+                double adj[4];
+                if (img_type >= 0 && img_type < USE_ASSET_THRESHOLD && !G::get_adjusted_image_rect(c, img_type, adj)) {
+                    const int key = type * 4 + (tw - f.tile_w0) + 2 * (th - f.tile_h0);
+                    f.tilekey[key] = 1;  // benign race: every writer stores 1
+                    f.cellmap[k] = (uint16_t)(0x4000 | key);
+                    continue;
+                }
+            }
+            int slot;
+#if defined(__CUDA_ARCH__)
+            slot = atomicAdd(&f.n_gen, 1);
+#else
+            slot = f.n_gen++;
+#endif
+            Blit b;
             double r[4] = {f.col_x[ci], f.row_y[cj], f.cell_w, f.cell_w};
             make_sprite_blit(c, f, b, r, 0, false, type, theme, 1.0f);
+            if (b.kind == BLIT_NONE)
+                continue;
+            *f.gen_blit(slot) = b;
+            f.cellmap[k] = (uint16_t)(CELL_GENERAL | slot);
+        }
+    }
+
+    // ---- phase C1a: arena space and a staging job for every tile the frame registered
+    static PG_HD void frame_tile_alloc(Ctx &c, Frame &f, const TileTable &tt, int tid, int nthreads) {
+        if (!G::DRAWS_GRID)
+            return;
+        const int gen_words = f.n_gen * (int)(sizeof(Blit) / 4);
+        for (int key = tid; key < CELL_KEYS; key += nthreads) {
+            if (f.tilekey[key] != 1)
+                continue;
+            const int type = key >> 2;
+            const int tw = f.tile_w0 + (key & 1), th = f.tile_h0 + ((key >> 1) & 1);
+            const int img_type = G::image_for_type(c, type);
+            const int theme = G::theme_for_grid_obj(c, type);
+            const int masked_theme = (c.h->options.restrict_themes && !G::should_preserve_type_themes(c, img_type)) ? 0 : theme;
+            const int slot = tt.texels ? c.assets->sprite_slot[img_type + masked_theme * MAX_ASSETS] : -1;
+            uint16_t code = 0xffffu;
+            if (slot >= 0) {
+                const int words = tile_words(tw, th);
+                int off, job;
+#if defined(__CUDA_ARCH__)
+                off = atomicAdd(&f.tile_top, words);
+#else
+                off = f.tile_top;
+                f.tile_top += words;
+#endif
+                if (off + words + gen_words <= Frame::kArenaWords) {
+#if defined(__CUDA_ARCH__)
+                    job = atomicAdd(&f.n_tjobs, 1);
+#else
+                    job = f.n_tjobs++;
+#endif
+                    if (job < MAX_TILE_JOBS) {
+                        f.tjob_src[job] = tt.index[(slot * MAX_TILE_DIM + (tw - 1)) * MAX_TILE_DIM + (th - 1)];
+                        f.tjob_dst[job] = (uint16_t)off;
+                        f.tjob_words[job] = (uint16_t)words;
+                        code = (uint16_t)(2 + off);
+                    }
+                }
+            }
+            f.tilekey[key] = code;
+        }
+    }
+
+    // ---- phase C1d: cells, pass B — tile cells learn where their tile was put; tiles that found
+    // no room (or have no table entry) fall back to a general blit
+    static PG_HD void frame_cells_finish(Ctx &c, Frame &f, int tid, int nthreads) {
+        if (!G::DRAWS_GRID)
+            return;
+        const int ncells = f.nx * f.ny;
+        for (int k = tid; k < ncells; k += nthreads) {
+            const uint16_t code = f.cellmap[k];
+            if ((code & 0xC000u) != 0x4000u)
+                continue;
+            const int key = code & 0x3fff;
+            const uint16_t tk = f.tilekey[key];
+            if (tk != 0xffffu) {
+                f.cellmap[k] = (uint16_t)(tk - 1);  // 1 + arena texel offset
+                continue;
+            }
+            f.cellmap[k] = 0;
+            int slot;
+#if defined(__CUDA_ARCH__)
+            slot = atomicAdd(&f.n_gen, 1);
+#else
+            slot = f.n_gen++;
+#endif
+            if ((slot + 1) * (int)(sizeof(Blit) / 4) + f.tile_top > Frame::kArenaWords) {
+                c.h->err |= ERR_BLIT_OVERFLOW;
+                continue;
+            }
+            const int ci = k / f.ny, cj = k - ci * f.ny;
+            const int type = key >> 2;
+            Blit b;
+            double r[4] = {f.col_x[ci], f.row_y[cj], f.cell_w, f.cell_w};
+            make_sprite_blit(c, f, b, r, 0, false, type, G::theme_for_grid_obj(c, type), 1.0f);
+            if (b.kind == BLIT_NONE)
+                continue;
+            *f.gen_blit(slot) = b;
+            f.cellmap[k] = (uint16_t)(CELL_GENERAL | slot);
         }
     }
 
@@ -1486,10 +1690,16 @@ struct Raster {
         }
     }
 
-    // ---- phase C2: per pixel row / column bit masks of the visible entity blits, so a pixel
-    // only walks the blits whose box really contains it (rowmask & colmask).
+    // the overlay blits (drawn after everything else) join the end of the entity list so the
+    // row / column masks cull them like any other blit; one thread, before frame_masks
+    static PG_HD void frame_append_overlays(Frame &f) {
+        for (int i = 0; i < f.n_overlay; i++) f.ents[f.n_ent + i] = f.overlay[i];
+    }
+
+    // ---- phase C2: per pixel row / column bit masks of the visible entity blits (+ overlays), so
+    // a pixel only walks the blits whose box really contains it (rowmask & colmask).
     static PG_HD void frame_masks(Frame &f, int tid, int nthreads) {
-        const int n = f.n_ent;
+        const int n = f.n_ent + f.n_overlay;
         for (int t = tid; t < RES_H + RES_W; t += nthreads) {
             const bool is_row = t < RES_H;
             const uint32_t q = (uint32_t)(is_row ? t : t - RES_H);
@@ -1518,76 +1728,204 @@ struct Raster {
         return __builtin_ctzll(m);
 #endif
     }
-
-    // ---- phase D: the gather. Returns 0xFFRRGGBB (Format_RGB32).
-    // A thread shades one pixel column (px fixed, py varies), so everything that depends on the
-    // column only is loaded once into a ColumnCtx and reused for all its rows.
-    struct ColumnCtx {
-        int nw;          // 64-blit mask words in use this frame: (n_ent + 63) / 64
-        int clo, chi;    // grid columns covering this pixel column (255 = none)
-        uint32_t bg_sx;  // full-screen background: source column of this pixel column
-        bool bg_full;
-    };
-    static PG_HD void column_begin(const Frame &f, int px, ColumnCtx &cc) {
-        cc.nw = (f.n_ent + 63) >> 6;
-        cc.clo = 255;
-        cc.chi = 0;
-        if (G::DRAWS_GRID) {
-            cc.clo = f.col_lo[px];
-            cc.chi = f.col_hi[px];
-        }
-        cc.bg_full = f.pad == 1;
-        cc.bg_sx = cc.bg_full ? (f.bg[0].basex + (uint32_t)f.bg[0].ix * (uint32_t)px) >> 16 : 0;
+    static PG_HD int top_bit64(uint64_t m) {  // m != 0
+#if defined(__CUDA_ARCH__)
+        return 63 - __clzll((long long)m);
+#else
+        return 63 - __builtin_clzll(m);
+#endif
     }
-    // entity blits [lo_bit, hi_bit) of the frame's list that contain the pixel, in list order
-    static PG_HD uint32_t shade_entities(const Frame &f, const ColumnCtx &cc, int px, int py, const uint32_t *atlas, uint32_t dst, int lo_bit,
-                                         int hi_bit) {
-        for (int w = lo_bit >> 6; w < cc.nw && w * 64 < hi_bit; w++) {
-            uint64_t m = f.ent_rowmask[py][w] & f.ent_colmask[px][w];
-            if (m == 0)
-                continue;  // the common case: no entity blit over this pixel
+
+    // ---- phase D: the gather. Colours are 0xFFRRGGBB (Format_RGB32).
+    // source value of cell (ci, cj) at a pixel; `code` = cellmap entry (non-zero)
+    static PG_HD uint32_t cell_layer(const Frame &f, uint32_t code, int ci, int cj, int px, int py, const uint32_t *atlas) {
+        if (code & CELL_GENERAL)
+            return blit_texel(*f.gen_blit((int)(code & 0x7fffu)), px, py, atlas, f.rot);
+        const int dx = px - f.col_p1[ci], dy = py - f.row_p1[cj];
+        return f.arena[(int)code - 1 + dy * f.col_tw[ci] + dx];
+    }
+
+    // Exact bottom-up composition of one pixel in draw order (draw_background, entities z=-1, grid
+    // cells x outer / y inner, entities z=0, z=1, overlays; basic-abstract-game.cpp:921-1007). The
+    // shader proper (shade_quad) walks the same layers top-down and falls back to this when a
+    // pixel stacks more translucent layers than it keeps in registers.
+    static PG_HD uint32_t shade_exact(const Frame &f, int px, int py, const uint32_t *atlas) {
+        uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
+        if (f.pad == 1) {
+            const Blit &b = f.bg[0];
+            dst = atlas[f.bgrow[py] + ((b.basex + (uint32_t)b.ix * (uint32_t)px) >> 16)];
+        } else {
+            for (int i = 0; i < f.n_bg; i++) dst = layer_over(dst, blit_texel(f.bg[i], px, py, atlas, f.rot));
+        }
+        const int nb = f.n_ent_below, n = f.n_ent + f.n_overlay;
+        for (int i = 0; i < nb; i++) dst = layer_over(dst, blit_texel(f.ents[i], px, py, atlas, f.rot));
+        if (G::DRAWS_GRID) {
+            const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
+            if (clo != 255 && rlo != 255) {
+                for (int ci = clo; ci <= chi; ci++)
+                    for (int cj = rlo; cj <= rhi; cj++) {
+                        const uint32_t code = f.cellmap[ci * f.ny + cj];
+                        if (code && px >= f.col_p1[ci] && px < f.col_p2[ci] && py >= f.row_p1[cj] && py < f.row_p2[cj])
+                            dst = layer_over(dst, cell_layer(f, code, ci, cj, px, py, atlas));
+                    }
+            }
+        }
+        for (int i = nb; i < n; i++) dst = layer_over(dst, blit_texel(f.ents[i], px, py, atlas, f.rot));
+        return dst;
+    }
+
+    // translucent layers met on the way down, deepest first after the walk (p0 = last pushed)
+    struct Partials {
+        uint32_t p0, p1, p2, p3;
+        bool overflow;
+    };
+    // returns true when the layer is opaque: the walk ends, `base` is the colour to blend onto
+    static PG_HD bool td_layer(Partials &a, uint32_t s, uint32_t &base) {
+        if (s >= 0xff000000u) {
+            base = s;
+            return true;
+        }
+        if (s != 0) {
+            if (a.p3 != 0)
+                a.overflow = true;
+            a.p3 = a.p2;
+            a.p2 = a.p1;
+            a.p1 = a.p0;
+            a.p0 = s;
+        }
+        return false;
+    }
+    static PG_HD uint32_t td_resolve(const Partials &a, uint32_t base) {
+        if (a.p0 != 0) base = a.p0 + pg_byte_mul(base, (~a.p0) >> 24);
+        if (a.p1 != 0) base = a.p1 + pg_byte_mul(base, (~a.p1) >> 24);
+        if (a.p2 != 0) base = a.p2 + pg_byte_mul(base, (~a.p2) >> 24);
+        if (a.p3 != 0) base = a.p3 + pg_byte_mul(base, (~a.p3) >> 24);
+        return base;
+    }
+
+    // What a thread keeps for the four pixel columns of its quad while it walks down the rows.
+    struct QuadCtx {
+        uint32_t ci[4];                    // colinfo
+        uint32_t bg_sx[4];                 // full-screen background: source column per pixel column
+        uint64_t cm[Frame::kEntWords];     // OR of the four column masks
+        int nw;                            // mask words in use this frame
+        int nb, n_all;                     // entity blits below the grid / all blits incl. overlays
+    };
+    static PG_HD void quad_begin(const Frame &f, int px0, QuadCtx &q) {
+        q.nb = f.n_ent_below;
+        q.n_all = f.n_ent + f.n_overlay;
+        q.nw = (q.n_all + 63) >> 6;
+        for (int k = 0; k < 4; k++) {
+            q.ci[k] = G::DRAWS_GRID ? f.colinfo[px0 + k] : 0u;
+            q.bg_sx[k] = f.pad == 1 ? (f.bg[0].basex + (uint32_t)f.bg[0].ix * (uint32_t)(px0 + k)) >> 16 : 0u;
+        }
+        for (int w = 0; w < Frame::kEntWords; w++)
+            q.cm[w] = w < q.nw ? (f.ent_colmask[px0][w] | f.ent_colmask[px0 + 1][w] | f.ent_colmask[px0 + 2][w] | f.ent_colmask[px0 + 3][w]) : 0;
+    }
+
+    // entity / overlay blits [lo_bit, hi_bit) that the row+quad masks let through, topmost first
+    static PG_HD bool td_entities(const Frame &f, Partials &a, uint32_t &base, const uint64_t *m, int px, int py, const uint32_t *atlas, int lo_bit,
+                                  int hi_bit) {
+        for (int w = Frame::kEntWords - 1; w >= 0; w--) {
+            uint64_t mw = m[w];
+            if (mw == 0 || w * 64 >= hi_bit || (w + 1) * 64 <= lo_bit)
+                continue;
             const int lo = lo_bit - w * 64, hi = hi_bit - w * 64;
             if (lo > 0)
-                m &= ~(((uint64_t)1 << lo) - 1);
+                mw &= ~(((uint64_t)1 << lo) - 1);
             if (hi < 64)
-                m &= ((uint64_t)1 << hi) - 1;
-            while (m) {
-                const int i = ctz64(m);
-                m &= m - 1;
-                dst = apply_blit(f.ents[w * 64 + i], px, py, dst, atlas, f.rot);
+                mw &= ((uint64_t)1 << hi) - 1;
+            while (mw) {
+                const int i = top_bit64(mw);
+                mw &= ~((uint64_t)1 << i);
+                if (td_layer(a, blit_texel(f.ents[w * 64 + i], px, py, atlas, f.rot), base))
+                    return true;
             }
         }
-        return dst;
+        return false;
     }
-    static PG_HD uint32_t shade_pixel(const Frame &f, const ColumnCtx &cc, int px, int py, const uint32_t *atlas) {
-        uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
-        if (cc.bg_full) {
-            const Blit &b = f.bg[0];
-            const uint32_t sy = (b.srcy + (uint32_t)b.iy * (uint32_t)py) >> 16;
-            dst = atlas[b.src + sy * b.sw + cc.bg_sx];  // RGB32 background: alpha 255, replaces dst
-        } else {
-            for (int i = 0; i < f.n_bg; i++) dst = apply_blit(f.bg[i], px, py, dst, atlas, f.rot);
-        }
-        // entities with render_z == -1 (the first n_ent_below of the list) go under the grid
-        const int nb = f.n_ent_below;
-        if (nb > 0)
-            dst = shade_entities(f, cc, px, py, atlas, dst, 0, nb);
-        if (G::DRAWS_GRID) {
-            const int rlo = f.row_lo[py], rhi = f.row_hi[py];
-            if (cc.clo != 255 && rlo != 255) {
-                for (int ci = cc.clo; ci <= cc.chi; ci++)
-                    for (int cj = rlo; cj <= rhi; cj++)
-                        dst = apply_blit(f.cells[ci * f.ny + cj], px, py, dst, atlas, f.rot);
+
+    // one pixel, top-down: overlays and entities above the grid, grid cells (last drawn first),
+    // entities below, background. `any_ent`: the row/quad masks are not empty (m valid).
+    static PG_HD uint32_t shade_td(const Frame &f, const QuadCtx &q, int k, int px, int py, uint32_t rowinfo, bool any_ent, const uint64_t *m,
+                                   const uint32_t *atlas) {
+        Partials a;
+        a.p0 = a.p1 = a.p2 = a.p3 = 0;
+        a.overflow = false;
+        uint32_t base = 0;
+        bool done = false;
+        if (any_ent)
+            done = td_entities(f, a, base, m, px, py, atlas, q.nb, q.n_all);
+        if (G::DRAWS_GRID && !done) {
+            const uint32_t ci = q.ci[k];
+            if (ci & rowinfo & CI_VALID) {
+                if (!((ci | rowinfo) & CI_MULTI)) {
+                    const uint32_t code = f.cellmap[(ci & CI_BASE_MASK) + (rowinfo & CI_BASE_MASK)];
+                    if (code) {
+                        uint32_t s;
+                        if (code & CELL_GENERAL) {
+                            s = blit_texel(*f.gen_blit((int)(code & 0x7fffu)), px, py, atlas, f.rot);
+                        } else {
+                            const int dx = (int)((ci >> CI_D_SHIFT) & 31u), dy = (int)((rowinfo >> CI_D_SHIFT) & 31u);
+                            s = f.arena[(int)code - 1 + dy * (int)((ci >> CI_TW_SHIFT) & 31u) + dx];
+                        }
+                        done = td_layer(a, s, base);
+                    }
+                } else {
+                    // a strip where neighbouring cells overlap: candidates in reverse draw order
+                    const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
+                    for (int cc = chi; cc >= clo && !done; cc--)
+                        for (int cj = rhi; cj >= rlo && !done; cj--) {
+                            const uint32_t code = f.cellmap[cc * f.ny + cj];
+                            if (code && px >= f.col_p1[cc] && px < f.col_p2[cc] && py >= f.row_p1[cj] && py < f.row_p2[cj])
+                                done = td_layer(a, cell_layer(f, code, cc, cj, px, py, atlas), base);
+                        }
+                }
             }
         }
-        dst = shade_entities(f, cc, px, py, atlas, dst, nb, f.n_ent);
-        for (int i = 0; i < f.n_overlay; i++) dst = apply_blit(f.overlay[i], px, py, dst, atlas, f.rot);
-        return dst;
+        if (!done && any_ent && q.nb > 0)
+            done = td_entities(f, a, base, m, px, py, atlas, 0, q.nb);
+        if (!done) {
+            if (f.pad == 1) {
+                base = atlas[f.bgrow[py] + q.bg_sx[k]];  // RGB32 background: alpha 255
+            } else {
+                base = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
+                for (int i = f.n_bg - 1; i >= 0; i--)
+                    if (td_layer(a, blit_texel(f.bg[i], px, py, atlas, f.rot), base))
+                        break;
+            }
+        }
+        if (a.overflow)
+            return shade_exact(f, px, py, atlas);
+        return td_resolve(a, base);
     }
-    static PG_HD uint32_t shade_pixel(const Frame &f, int px, int py, const uint32_t *atlas) {
-        ColumnCtx cc;
-        column_begin(f, px, cc);
-        return shade_pixel(f, cc, px, py, atlas);
+
+    // Four horizontally adjacent pixels of row py -> 12 packed RGB bytes (3 words) at out[0..2]:
+    // bgr32_to_rgb888 (game.cpp:8-23) fused into the shader.
+    static PG_HD void shade_quad(const Frame &f, const QuadCtx &q, int px0, int py, const uint32_t *atlas, uint32_t *out) {
+        uint64_t m[Frame::kEntWords];
+        uint64_t any = 0;
+        for (int w = 0; w < Frame::kEntWords; w++) {
+            m[w] = w < q.nw ? (f.ent_rowmask[py][w] & q.cm[w]) : 0;
+            any |= m[w];
+        }
+        const uint32_t rowinfo = G::DRAWS_GRID ? f.rowinfo[py] : 0u;
+        uint32_t c[4];
+        for (int k = 0; k < 4; k++) c[k] = shade_td(f, q, k, px0 + k, py, rowinfo, any != 0, m, atlas);
+        // 0xAARRGGBB -> bytes R,G,B
+#if defined(__CUDA_ARCH__)
+        out[0] = __byte_perm(c[0], c[1], 0x6012);
+        out[1] = __byte_perm(c[1], c[2], 0x5601);
+        out[2] = __byte_perm(c[2], c[3], 0x4560);
+#else
+        const uint32_t r0 = (c[0] >> 16) & 0xff, g0 = (c[0] >> 8) & 0xff, b0 = c[0] & 0xff;
+        const uint32_t r1 = (c[1] >> 16) & 0xff, g1 = (c[1] >> 8) & 0xff, b1 = c[1] & 0xff;
+        const uint32_t r2 = (c[2] >> 16) & 0xff, g2 = (c[2] >> 8) & 0xff, b2 = c[2] & 0xff;
+        const uint32_t r3 = (c[3] >> 16) & 0xff, g3 = (c[3] >> 8) & 0xff, b3 = c[3] & 0xff;
+        out[0] = r0 | (g0 << 8) | (b0 << 16) | (r1 << 24);
+        out[1] = g1 | (b1 << 8) | (r2 << 16) | (g2 << 24);
+        out[2] = b2 | (r3 << 8) | (g3 << 16) | (b3 << 24);
+#endif
     }
 };
 

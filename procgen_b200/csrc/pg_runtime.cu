@@ -183,6 +183,15 @@ static int32_t fnv1a(const char *str) {
     return (int32_t)hash;
 }
 
+// ================================================================= pre-scaled tile table
+#ifndef PG_HOSTSIM
+// one CTA per (sprite slot, tw, th)
+__global__ void tile_table_kernel(const SpriteDesc *sprites, const uint32_t *index, uint32_t *texels, const uint32_t *atlas) {
+    const int slot = (int)blockIdx.x / TILE_VARIANTS, v = (int)blockIdx.x % TILE_VARIANTS;
+    tile_table_fill(sprites, index, texels, atlas, slot, v / MAX_TILE_DIM + 1, v % MAX_TILE_DIM + 1, (int)threadIdx.x, (int)blockDim.x);
+}
+#endif
+
 // ================================================================= VecEnv (VecGame, vecgame.h)
 struct VecEnv {
     int num_envs = 0;
@@ -194,6 +203,8 @@ struct VecEnv {
     KParams base{};                  // common launch parameters
     std::vector<GameAssets *> d_assets;  // per joint game
     uint32_t *d_atlas = nullptr;
+    uint32_t *d_tile_texels = nullptr, *d_tile_index = nullptr;
+    SpriteDesc *d_tile_sprites = nullptr;
     uint32_t *d_lvl_seeds = nullptr;
     int32_t *d_action = nullptr;
     bool initial_reset_done = false;
@@ -581,6 +592,39 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
             copy_to_dev(d, &tables[g], sizeof(GameAssets));
             v->d_assets.push_back(d);
         }
+        // pre-scaled cell tiles of every sprite (pg_raster.cuh TileTable), filled on the device by
+        // the general blit path's own arithmetic
+        const bool want_tiles = !(getenv("PGB200_NO_TILES") && atoi(getenv("PGB200_NO_TILES")) != 0);
+        const int S = (int)atlas.tile_sprites.size();
+        if (want_tiles && S > 0) {
+            std::vector<uint32_t> index((size_t)S * TILE_VARIANTS);
+            size_t top = 0;
+            for (int sl = 0; sl < S; sl++)
+                for (int tw = 1; tw <= MAX_TILE_DIM; tw++)
+                    for (int th = 1; th <= MAX_TILE_DIM; th++) {
+                        index[((size_t)sl * MAX_TILE_DIM + (tw - 1)) * MAX_TILE_DIM + (th - 1)] = (uint32_t)top;
+                        top += (size_t)tile_words(tw, th);
+                    }
+            if (top >= (size_t)1 << 32)
+                throw std::runtime_error("tile table too large");
+            v->d_tile_index = dev_alloc<uint32_t>(index.size());
+            copy_to_dev(v->d_tile_index, index.data(), index.size() * sizeof(uint32_t));
+            v->d_tile_sprites = dev_alloc<SpriteDesc>((size_t)S);
+            copy_to_dev(v->d_tile_sprites, atlas.tile_sprites.data(), (size_t)S * sizeof(SpriteDesc));
+            v->d_tile_texels = dev_alloc<uint32_t>(top);
+#ifndef PG_HOSTSIM
+            tile_table_kernel<<<S * TILE_VARIANTS, 64>>>(v->d_tile_sprites, v->d_tile_index, v->d_tile_texels, v->d_atlas);
+            CUDA_CHECK(cudaGetLastError());
+#else
+            for (int sl = 0; sl < S; sl++)
+                for (int vv = 0; vv < TILE_VARIANTS; vv++)
+                    tile_table_fill(v->d_tile_sprites, v->d_tile_index, v->d_tile_texels, v->d_atlas, sl, vv / MAX_TILE_DIM + 1, vv % MAX_TILE_DIM + 1, 0, 1);
+#endif
+            v->base.tiles.texels = v->d_tile_texels;
+            v->base.tiles.index = v->d_tile_index;
+            v->base.tiles.sprites = v->d_tile_sprites;
+            v->base.tiles.n_slots = S;
+        }
     } catch (const std::exception &e) {
         pg_fatal("failed to load images %s\n", e.what());
     }
@@ -655,6 +699,11 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     p.options.distribution_mode = dist_mode;
     p.snap = snap ? 1 : 0;
     p.env_global_offset = env_index_offset;
+#ifndef PG_HOSTSIM
+    // every upload and memset above ran on the legacy default stream; the step kernels run on
+    // non-blocking streams that do not order against it
+    CUDA_CHECK(cudaDeviceSynchronize());
+#endif
     return (libenv_env *)v;
 }
 
@@ -813,6 +862,9 @@ void libenv_close(libenv_env *handle) {
     if (p.rot_scratch)
         dev_free(p.rot_scratch);
     dev_free(v->d_atlas);
+    dev_free(v->d_tile_texels);
+    dev_free(v->d_tile_index);
+    dev_free(v->d_tile_sprites);
     dev_free(v->d_action);
     dev_free(p.rgb);
     dev_free(p.rew);
@@ -1029,6 +1081,9 @@ void set_state(libenv_env *handle, int env_idx, char *data, int length) {
         pg_fatal("set_state: %s\n", ex.what());
     }
     store_env(v, env_idx, e);
+#ifndef PG_HOSTSIM
+    CUDA_CHECK(cudaDeviceSynchronize());  // the uploads ran on the legacy stream; the kernels below do not order against it
+#endif
     // Game::observe(): re-render this env and rewrite its rew / first / info slots from the restored step_data
     KParams p = v->base;
     p.assets = v->d_assets[gi];
@@ -1040,6 +1095,15 @@ void set_state(libenv_env *handle, int env_idx, char *data, int length) {
     g->observe_only(p, lc);
     v->sync();
     v->rgb_copy_enqueued = false;  // a DMA started behind the last step predates this frame: observe copies again
+}
+
+int pgb200_frame_info(const char *game, int *frame_bytes, int *ctas_per_sm) {
+    const GameVTable *g = find_game(game);
+    if (!g)
+        return -1;
+    *frame_bytes = g->frame_bytes;
+    *ctas_per_sm = g->render_ctas_per_sm;
+    return 0;
 }
 
 int64_t pgb200_kernel_launches(libenv_env *handle) { return ((VecEnv *)handle)->launches; }

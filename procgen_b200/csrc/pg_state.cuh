@@ -147,6 +147,7 @@ struct GameAssets {
     SpriteDesc backgrounds[MAX_BACKGROUNDS];             // RGB32
     int32_t num_backgrounds;
     int32_t pad[3];
+    int16_t sprite_slot[MAX_ASSETS * MAX_IMAGE_THEMES];  // row of the pre-scaled tile table (pg_raster.cuh TileTable), -1 = none
 };
 
 // Handle a thread uses to reach one env. Pointers are generic (global or shared).

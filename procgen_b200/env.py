@@ -72,6 +72,21 @@ def create_random_seed():
     return rand_seed
 
 
+def _broadcast_seed(seed):
+    try:
+        import torch
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.tensor([seed], dtype=torch.int64, device=dev)
+            dist.broadcast(t, src=0)
+            return int(t.item())
+    except Exception:
+        pass
+    raise ValueError("shard=(rank, world) needs an explicit rand_seed when torch.distributed is not initialised")
+
+
 class _CudaArray:
     """Minimal __cuda_array_interface__ holder so torch can alias library-owned HBM."""
 
@@ -98,6 +113,10 @@ class BaseProcgenEnv:
             raise NotImplementedError("render_mode='rgb_array' (512x512 antialiased info['rgb']) is out of scope")
         if rand_seed is None:
             rand_seed = create_random_seed()
+            if shard is not None:
+                # every shard of one logical VecGame must replay the SAME per-env seed chain
+                # (vecgame.cpp:301-314): take rank 0's draw instead of de-correlating per rank
+                rand_seed = _broadcast_seed(rand_seed)
         if resource_root is None:
             resource_root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data") + os.sep
 
@@ -226,17 +245,33 @@ class BaseProcgenEnv:
             else:
                 host = torch.as_tensor(np.asarray(ac).astype(np.int32))
                 if self._pinned_ac is None:
-                    self._pinned_ac = torch.empty(self.num, dtype=torch.int32, pin_memory=True)
-                self._pinned_ac.copy_(host)
-                self._ac.copy_(self._pinned_ac, non_blocking=True)
+                    # two pinned staging buffers, each guarded by an event recorded behind its H2D copy:
+                    # act() never rewrites host memory a still-queued DMA is going to read
+                    self._pinned_ac = [torch.empty(self.num, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+                    self._pinned_ev = [torch.cuda.Event(), torch.cuda.Event()]
+                    self._pinned_used = [False, False]
+                    self._pinned_i = 0
+                i = self._pinned_i
+                self._pinned_i = 1 - i
+                if self._pinned_used[i]:
+                    self._pinned_ev[i].synchronize()
+                self._pinned_ac[i].copy_(host)
+                self._ac.copy_(self._pinned_ac[i], non_blocking=True)
+                self._pinned_ev[i].record(torch.cuda.current_stream(self._dev))
+                self._pinned_used[i] = True
             self._lib.pgb200_act_device(self._h)
 
     def get_info(self) -> List[dict]:
+        """gym3's list-of-dicts form (env.py:128-136). One D2H copy for all three columns; callers on
+        the hot path should use get_info_tensors() (columns, no copy) instead."""
         if self._host_buffers:
-            cols = {k: v for k, v in self._info.items()}
+            cols = [self._info[k].tolist() for k in self._info_names]
         else:
-            cols = {k: v.cpu().numpy() for k, v in self._info.items()}
-        return [{k: cols[k][i] for k in self._info_names} for i in range(self.num)]
+            torch = self._torch
+            packed = torch.stack([self._info[k].to(torch.int32) for k in self._info_names]).cpu().numpy()
+            cols = [packed[0].tolist(), packed[1].astype(np.uint8).tolist(), packed[2].tolist()]
+        a, b, c3 = self._info_names
+        return [{a: x, b: y, c3: z} for x, y, z in zip(*cols)]
 
     def get_info_tensors(self):
         """Column form of get_info() without a host copy."""
@@ -322,6 +357,9 @@ class BaseProcgenEnv:
             return out
         dist.gather(self._rgb, None, dst=dst)
         return None
+
+    def gather_how(self) -> str:
+        return "torch.distributed.gather (NCCL) of the rgb shard after the step"
 
     def close(self):
         if getattr(self, "_h", None):

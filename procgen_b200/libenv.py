@@ -47,7 +47,8 @@ class DeviceBuffers(C.Structure):
 EXPORTS = ["libenv_version", "libenv_make", "libenv_get_tensortypes", "libenv_set_buffers", "libenv_observe",
            "libenv_act", "libenv_close", "pgb200_get_device_buffers", "pgb200_set_stream", "pgb200_act_device",
            "pgb200_sync", "pgb200_get_errors", "pgb200_debug_cycles", "pgb200_debug_read_env", "pgb200_kernel_launches", "pgb200_is_device_build",
-           "pgb200_kernel_timing_begin", "pgb200_kernel_timing_end", "get_state", "set_state", "pgb200_set_launch_shape"]
+           "pgb200_kernel_timing_begin", "pgb200_kernel_timing_end", "get_state", "set_state", "pgb200_set_launch_shape",
+           "pgb200_frame_info"]
 
 _lib = None
 
@@ -73,6 +74,8 @@ def bind(lib):
     lib.pgb200_debug_cycles.restype = C.c_int
     lib.pgb200_debug_read_env.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     lib.pgb200_debug_read_env.restype = C.c_int
+    lib.pgb200_frame_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.pgb200_frame_info.restype = C.c_int
     lib.pgb200_kernel_launches.argtypes = [C.c_void_p]
     lib.pgb200_kernel_launches.restype = C.c_int64
     lib.get_state.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
