@@ -18,7 +18,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",          # the reference wheels are built without FMA (CMakeLists.txt:30)
-    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC", "-Xfatbin", "-compress-all",
 ]
 HOSTSIM_FLAGS = ["-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fPIC", "-DPG_HOSTSIM", "-x", "c++"]
 
