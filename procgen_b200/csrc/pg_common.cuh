@@ -19,10 +19,13 @@
 #if defined(__CUDACC__)
 #define PG_HD __host__ __device__ __forceinline__
 #define PG_HD_NOINLINE __host__ __device__ __noinline__
+// free (non-member, non-template) functions defined in headers: `inline` for linkage, never inlined on the device
+#define PG_HD_FREE_NOINLINE inline __host__ __device__ __noinline__
 #define PG_D __device__ __forceinline__
 #else
 #define PG_HD inline
 #define PG_HD_NOINLINE
+#define PG_HD_FREE_NOINLINE inline
 #define PG_D inline
 #endif
 

@@ -139,7 +139,7 @@ struct FrameT {
     uint32_t colinfo[RES_W], rowinfo[RES_H];  // CI_* words
     uint32_t bgrow[RES_H];                    // pad == 1: atlas offset of the background row sampled by pixel row py
     uint16_t cellmap[MAX_CELLS_1D * MAX_CELLS_1D];  // [ci * ny + cj], x outer / y inner = draw order
-    uint16_t tilekey[MAX_CELLS_1D > 1 ? CELL_KEYS : 4];  // per (type, size variant): 0 unused | 1 wanted | 2 + arena texel offset | 0xffff unavailable
+    alignas(4) uint16_t tilekey[MAX_CELLS_1D > 1 ? CELL_KEYS : 4];  // per (type, size variant): 0 unused | 1 wanted | 2 + arena texel offset | 0xffff unavailable
     uint32_t tjob_src[MAX_TILE_JOBS];         // tile copies to stage: texel offset in the table,
     uint16_t tjob_dst[MAX_TILE_JOBS], tjob_words[MAX_TILE_JOBS];  // arena word offset, words
     // tiled entities only reserve their blit slots while the list is built; the tiles themselves
@@ -161,7 +161,7 @@ PG_HD void blit_clear(Blit &b) {
     b.kind = BLIT_NONE;
 }
 
-PG_HD void make_image_blit(Blit &b, double tx, double ty, double tw, double th, SpriteDesc sd, bool mirror, int int_opacity, bool snap) {
+PG_HD_FREE_NOINLINE void make_image_blit(Blit &b, double tx, double ty, double tw, double th, SpriteDesc sd, bool mirror, int int_opacity, bool snap) {
     blit_clear(b);
     const int sw = sd.w, sh = sd.h;
     if (sw <= 0 || sh <= 0)
@@ -556,7 +556,7 @@ PG_HD void rot_transform_image(RotBlit &rb, int sw, int sh, const double *r, con
 }
 
 // QRasterPaintEngine::drawImage under a rotating matrix: fills rb, returns false if nothing drawn
-PG_HD void rot_draw(RotBlit &rb, int sw, int sh, const double *r, const RotXform &m) {
+PG_HD_FREE_NOINLINE void rot_draw(RotBlit &rb, int sw, int sh, const double *r, const RotXform &m) {
     rb.pad = 0;  // row window [lo, hi) the spans can fall in: lo | hi << 8 (set below)
     rb.absolute = 0;
     rb.dudx = rb.dvdx = rb.dudy = rb.dvdy = rb.u0 = rb.v0 = 0;
@@ -618,7 +618,7 @@ PG_HD void rot_draw(RotBlit &rb, int sw, int sh, const double *r, const RotXform
 }
 
 // ---- rule F: opaque fillRect
-PG_HD void make_solid_blit(Blit &b, double x, double y, double w, double h, uint32_t rgb) {
+PG_HD_FREE_NOINLINE void make_solid_blit(Blit &b, double x, double y, double w, double h, uint32_t rgb) {
     int x1 = pg_qround(x), y1 = pg_qround(y);
     int x2 = pg_qround(x + w), y2 = pg_qround(y + h);
     if (x2 < x1) { int t = x1; x1 = x2; x2 = t; }
@@ -661,11 +661,9 @@ PG_HD uint32_t layer_of(uint32_t src, int int_opacity) {
     return pg_byte_mul(src, (uint32_t)((int_opacity * 255) >> 8));
 }
 
-#if defined(PG_APPLY_NOINLINE) && defined(__CUDACC__)
-__host__ __device__ __noinline__ uint32_t blit_texel(const Blit &b, int px, int py, const uint32_t *atlas, const RotBlit *rots) {
-#else
-PG_HD uint32_t blit_texel(const Blit &b, int px, int py, const uint32_t *atlas, const RotBlit *rots) {
-#endif
+// Out of line on the device: it is the rare path of the shader, and inlined at its dozen call sites
+// it made the render kernel ten times the size of the instruction cache.
+PG_HD_FREE_NOINLINE uint32_t blit_texel(const Blit &b, int px, int py, const uint32_t *atlas, const RotBlit *rots) {
     const uint32_t box = *reinterpret_cast<const uint32_t *>(&b);  // x1 | y1<<8 | w<<16 | h<<24
     const uint32_t dx = (uint32_t)px - (box & 0xffu);
     const uint32_t dy = (uint32_t)py - ((box >> 8) & 0xffu);
@@ -962,8 +960,8 @@ struct Raster {
     }
 
     // draw_image (basic-abstract-game.cpp:877-913) for the un-rotated, un-tiled case
-    static PG_HD void make_sprite_blit(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
-                                       int defer_ei = -1) {
+    static PG_HD_NOINLINE void make_sprite_blit(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
+                                                int defer_ei = -1) {
         blit_clear(b);
         int img_type = G::image_for_type(c, base_type);
         if (img_type < 0)
@@ -1071,7 +1069,7 @@ struct Raster {
     }
 
     // draw_image's inner part for an already-resolved image type and already-adjusted rect
-    static PG_HD void make_sprite_blit_noadjust(Ctx &c, Frame &f, Blit &b, double *rect, bool is_reflected, int img_type, int theme, float alpha) {
+    static PG_HD_NOINLINE void make_sprite_blit_noadjust(Ctx &c, Frame &f, Blit &b, double *rect, bool is_reflected, int img_type, int theme, float alpha) {
         blit_clear(b);
         if (theme < 0 || theme >= MAX_IMAGE_THEMES) {
             c.h->err |= ERR_FASSERT;
@@ -1749,7 +1747,7 @@ struct Raster {
     // cells x outer / y inner, entities z=0, z=1, overlays; basic-abstract-game.cpp:921-1007). The
     // shader proper (shade_quad) walks the same layers top-down and falls back to this when a
     // pixel stacks more translucent layers than it keeps in registers.
-    static PG_HD uint32_t shade_exact(const Frame &f, int px, int py, const uint32_t *atlas) {
+    static PG_HD_NOINLINE uint32_t shade_exact(const Frame &f, int px, int py, const uint32_t *atlas) {
         uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
         if (f.pad == 1) {
             const Blit &b = f.bg[0];
@@ -1803,32 +1801,11 @@ struct Raster {
         return base;
     }
 
-    // What a thread keeps for the four pixel columns of its quad while it walks down the rows.
-    struct QuadCtx {
-        uint32_t ci[4];                    // colinfo
-        uint32_t bg_sx[4];                 // full-screen background: source column per pixel column
-        uint64_t cm[Frame::kEntWords];     // OR of the four column masks
-        int nw;                            // mask words in use this frame
-        int nb, n_all;                     // entity blits below the grid / all blits incl. overlays
-    };
-    static PG_HD void quad_begin(const Frame &f, int px0, QuadCtx &q) {
-        q.nb = f.n_ent_below;
-        q.n_all = f.n_ent + f.n_overlay;
-        q.nw = (q.n_all + 63) >> 6;
-        for (int k = 0; k < 4; k++) {
-            q.ci[k] = G::DRAWS_GRID ? f.colinfo[px0 + k] : 0u;
-            q.bg_sx[k] = f.pad == 1 ? (f.bg[0].basex + (uint32_t)f.bg[0].ix * (uint32_t)(px0 + k)) >> 16 : 0u;
-        }
-        for (int w = 0; w < Frame::kEntWords; w++)
-            q.cm[w] = w < q.nw ? (f.ent_colmask[px0][w] | f.ent_colmask[px0 + 1][w] | f.ent_colmask[px0 + 2][w] | f.ent_colmask[px0 + 3][w]) : 0;
-    }
-
-    // entity / overlay blits [lo_bit, hi_bit) that the row+quad masks let through, topmost first
-    static PG_HD bool td_entities(const Frame &f, Partials &a, uint32_t &base, const uint64_t *m, int px, int py, const uint32_t *atlas, int lo_bit,
-                                  int hi_bit) {
-        for (int w = Frame::kEntWords - 1; w >= 0; w--) {
-            uint64_t mw = m[w];
-            if (mw == 0 || w * 64 >= hi_bit || (w + 1) * 64 <= lo_bit)
+    // entity / overlay blits [lo_bit, hi_bit) whose row and column masks contain the pixel, topmost first
+    static PG_HD bool td_entities(const Frame &f, Partials &a, uint32_t &base, int px, int py, const uint32_t *atlas, int lo_bit, int hi_bit) {
+        for (int w = (hi_bit - 1) >> 6; w >= (lo_bit >> 6); w--) {
+            uint64_t mw = f.ent_rowmask[py][w] & f.ent_colmask[px][w];
+            if (mw == 0)
                 continue;
             const int lo = lo_bit - w * 64, hi = hi_bit - w * 64;
             if (lo > 0)
@@ -1845,49 +1822,35 @@ struct Raster {
         return false;
     }
 
-    // one pixel, top-down: overlays and entities above the grid, grid cells (last drawn first),
-    // entities below, background. `any_ent`: the row/quad masks are not empty (m valid).
-    static PG_HD uint32_t shade_td(const Frame &f, const QuadCtx &q, int k, int px, int py, uint32_t rowinfo, bool any_ent, const uint64_t *m,
-                                   const uint32_t *atlas) {
+    // One pixel, every layer, top-down: overlays and entities above the grid, grid cells (last drawn
+    // first), entities below, background. Out of line: the shader proper (shade_quad) only calls it
+    // for pixels that have more than "at most one tile cell over a full-screen background".
+    static PG_HD_NOINLINE uint32_t shade_generic(const Frame &f, int px, int py, const uint32_t *atlas) {
         Partials a;
         a.p0 = a.p1 = a.p2 = a.p3 = 0;
         a.overflow = false;
         uint32_t base = 0;
+        const int nb = f.n_ent_below, n_all = f.n_ent + f.n_overlay;
         bool done = false;
-        if (any_ent)
-            done = td_entities(f, a, base, m, px, py, atlas, q.nb, q.n_all);
+        if (n_all > nb)
+            done = td_entities(f, a, base, px, py, atlas, nb, n_all);
         if (G::DRAWS_GRID && !done) {
-            const uint32_t ci = q.ci[k];
-            if (ci & rowinfo & CI_VALID) {
-                if (!((ci | rowinfo) & CI_MULTI)) {
-                    const uint32_t code = f.cellmap[(ci & CI_BASE_MASK) + (rowinfo & CI_BASE_MASK)];
-                    if (code) {
-                        uint32_t s;
-                        if (code & CELL_GENERAL) {
-                            s = blit_texel(*f.gen_blit((int)(code & 0x7fffu)), px, py, atlas, f.rot);
-                        } else {
-                            const int dx = (int)((ci >> CI_D_SHIFT) & 31u), dy = (int)((rowinfo >> CI_D_SHIFT) & 31u);
-                            s = f.arena[(int)code - 1 + dy * (int)((ci >> CI_TW_SHIFT) & 31u) + dx];
-                        }
-                        done = td_layer(a, s, base);
+            const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
+            if (clo != 255 && rlo != 255) {
+                for (int cc = chi; cc >= clo && !done; cc--)
+                    for (int cj = rhi; cj >= rlo && !done; cj--) {
+                        const uint32_t code = f.cellmap[cc * f.ny + cj];
+                        if (code && px >= f.col_p1[cc] && px < f.col_p2[cc] && py >= f.row_p1[cj] && py < f.row_p2[cj])
+                            done = td_layer(a, cell_layer(f, code, cc, cj, px, py, atlas), base);
                     }
-                } else {
-                    // a strip where neighbouring cells overlap: candidates in reverse draw order
-                    const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
-                    for (int cc = chi; cc >= clo && !done; cc--)
-                        for (int cj = rhi; cj >= rlo && !done; cj--) {
-                            const uint32_t code = f.cellmap[cc * f.ny + cj];
-                            if (code && px >= f.col_p1[cc] && px < f.col_p2[cc] && py >= f.row_p1[cj] && py < f.row_p2[cj])
-                                done = td_layer(a, cell_layer(f, code, cc, cj, px, py, atlas), base);
-                        }
-                }
             }
         }
-        if (!done && any_ent && q.nb > 0)
-            done = td_entities(f, a, base, m, px, py, atlas, 0, q.nb);
+        if (!done && nb > 0)
+            done = td_entities(f, a, base, px, py, atlas, 0, nb);
         if (!done) {
             if (f.pad == 1) {
-                base = atlas[f.bgrow[py] + q.bg_sx[k]];  // RGB32 background: alpha 255
+                const Blit &b = f.bg[0];
+                base = atlas[f.bgrow[py] + ((b.basex + (uint32_t)b.ix * (uint32_t)px) >> 16)];  // RGB32 background: alpha 255
             } else {
                 base = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
                 for (int i = f.n_bg - 1; i >= 0; i--)
@@ -1900,18 +1863,61 @@ struct Raster {
         return td_resolve(a, base);
     }
 
-    // Four horizontally adjacent pixels of row py -> 12 packed RGB bytes (3 words) at out[0..2]:
-    // bgr32_to_rgb888 (game.cpp:8-23) fused into the shader.
-    static PG_HD void shade_quad(const Frame &f, const QuadCtx &q, int px0, int py, const uint32_t *atlas, uint32_t *out) {
-        uint64_t m[Frame::kEntWords];
-        uint64_t any = 0;
-        for (int w = 0; w < Frame::kEntWords; w++) {
-            m[w] = w < q.nw ? (f.ent_rowmask[py][w] & q.cm[w]) : 0;
-            any |= m[w];
+    // What a thread keeps for the four pixel columns of its quad while it walks down the rows.
+    struct QuadCtx {
+        uint32_t ci[4];                    // colinfo
+        uint32_t bg_sx[4];                 // full-screen background: source column per pixel column
+        uint64_t cm[Frame::kEntWords];     // OR of the four column masks
+        int nw;                            // mask words in use this frame
+        bool bg_full;
+    };
+    static PG_HD void quad_begin(const Frame &f, int px0, QuadCtx &q) {
+        q.nw = (f.n_ent + f.n_overlay + 63) >> 6;
+        q.bg_full = f.pad == 1;
+        for (int k = 0; k < 4; k++) {
+            q.ci[k] = G::DRAWS_GRID ? f.colinfo[px0 + k] : 0u;
+            q.bg_sx[k] = q.bg_full ? (f.bg[0].basex + (uint32_t)f.bg[0].ix * (uint32_t)(px0 + k)) >> 16 : 0u;
         }
+        for (int w = 0; w < Frame::kEntWords; w++)
+            q.cm[w] = w < q.nw ? (f.ent_colmask[px0][w] | f.ent_colmask[px0 + 1][w] | f.ent_colmask[px0 + 2][w] | f.ent_colmask[px0 + 3][w]) : 0;
+    }
+
+    // Four horizontally adjacent pixels of row py -> 12 packed RGB bytes (3 words) at out[0..2]:
+    // bgr32_to_rgb888 (game.cpp:8-23) fused into the shader. The inline part covers the common
+    // pixel — no entity blit near, at most one cell and that one from a pre-scaled tile, full-screen
+    // background: tile texel first, background fetched only when the texel is not opaque.
+    static PG_HD void shade_quad(const Frame &f, const QuadCtx &q, int px0, int py, const uint32_t *atlas, uint32_t *out) {
+        uint64_t any = 0;
+        for (int w = 0; w < Frame::kEntWords; w++)
+            if (w < q.nw)
+                any |= f.ent_rowmask[py][w] & q.cm[w];
         const uint32_t rowinfo = G::DRAWS_GRID ? f.rowinfo[py] : 0u;
+        const uint32_t bgrow = q.bg_full ? f.bgrow[py] : 0u;
         uint32_t c[4];
-        for (int k = 0; k < 4; k++) c[k] = shade_td(f, q, k, px0 + k, py, rowinfo, any != 0, m, atlas);
+        for (int k = 0; k < 4; k++) {
+            const uint32_t ci = q.ci[k];
+            bool slow = any != 0 || !q.bg_full;
+            uint32_t s = 0;
+            if (G::DRAWS_GRID && !slow && (ci & rowinfo & CI_VALID)) {
+                if ((ci | rowinfo) & CI_MULTI) {
+                    slow = true;
+                } else {
+                    const uint32_t code = f.cellmap[(ci & CI_BASE_MASK) + (rowinfo & CI_BASE_MASK)];
+                    if (code & CELL_GENERAL)
+                        slow = true;
+                    else if (code)
+                        s = f.arena[(int)code - 1 + (int)((rowinfo >> CI_D_SHIFT) & 31u) * (int)((ci >> CI_TW_SHIFT) & 31u) + (int)((ci >> CI_D_SHIFT) & 31u)];
+                }
+            }
+            if (slow) {
+                c[k] = shade_generic(f, px0 + k, py, atlas);
+            } else if (s >= 0xff000000u) {
+                c[k] = s;
+            } else {
+                const uint32_t bg = atlas[bgrow + q.bg_sx[k]];
+                c[k] = s != 0 ? s + pg_byte_mul(bg, (~s) >> 24) : bg;
+            }
+        }
         // 0xAARRGGBB -> bytes R,G,B
 #if defined(__CUDA_ARCH__)
         out[0] = __byte_perm(c[0], c[1], 0x6012);

@@ -1,4 +1,6 @@
 """Shared test helpers: lockstep comparison of any libenv-ABI implementation against the oracle."""
+import os
+
 import numpy as np
 
 from oracle.ref_env import RefVecEnv, default_pack, mt19937_actions
@@ -76,3 +78,28 @@ def run_state_roundtrip(make_ref, make_dut, num, steps, check_every=25):
     assert [ref2.get_state(e) for e in range(num)] == [dut2.get_state(e) for e in range(num)]
     for env in (ref, dut, ref2, dut2):
         env.close()
+
+
+SNAP_SCRIPT = r"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from helpers import make_pair, run_lockstep
+for name, mode in [("coinrun", "hard"), ("maze", "hard"), ("bigfish", "hard"), ("heist", "hard"), ("fruitbot", "hard")]:
+    ref, dut = make_pair({lib!r}, 8, name, extra_options={{"snap_target_rect": False}}, distribution_mode=mode,
+                         num_levels=200, start_level=0, rand_seed=0)
+    run_lockstep(ref, dut, 200)
+    ref.close(); dut.close()
+print("SNAP_OFF_OK")
+"""
+
+
+def run_snap_off_lockstep(lib):
+    """The Qt-5-style un-snapped target rect (the known Qt 5 / Qt 6 risk) is a switch in both
+    implementations; the oracle reads it from the environment once per process, hence the subprocess."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QT_SHIM_SNAP="0")
+    out = subprocess.run([sys.executable, "-c", SNAP_SCRIPT.format(root=root, lib=lib)], env=env, capture_output=True, text=True)
+    assert "SNAP_OFF_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

@@ -137,3 +137,10 @@ def test_sharded_seed_chain_matches_unsharded(ref_lib, hostsim_lib):
         assert np.array_equal(ref.info["level_seed"][8:], shard.info["level_seed"])
     ref.close()
     shard.close()
+
+
+def test_unsnapped_target_rect_bit_exact(ref_lib, hostsim_lib):
+    """snap_target_rect=False (Qt-5-style phase): every cell and sprite takes the general blit path."""
+    from helpers import run_snap_off_lockstep
+
+    run_snap_off_lockstep(hostsim_lib)

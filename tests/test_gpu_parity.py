@@ -169,3 +169,136 @@ def test_full_size_properties(ref_lib, product_lib, name, mode, n_big, steps):
         assert np.array_equal(heads[t][1], ob["rgb"]), f"step {t}"
         assert np.array_equal(heads[t][2], first.astype(bool)), f"step {t}"
     ref.close()
+
+
+# ------------------------------------------------------------------ round 2: holes named by the review
+OTHER_MODES = [
+    ("maze", "memory", 8, 300), ("heist", "memory", 8, 300), ("miner", "memory", 8, 300), ("caveflyer", "memory", 8, 300),
+    ("jumper", "memory", 8, 300), ("leaper", "extreme", 8, 300), ("chaser", "extreme", 8, 300), ("dodgeball", "extreme", 8, 300),
+    ("ninja", "easy", 16, 300), ("fruitbot", "easy", 16, 300), ("bossfight", "easy", 8, 300), ("climber", "easy", 16, 300),
+    ("miner", "easy", 16, 300), ("plunder", "easy", 16, 300), ("caveflyer", "easy", 16, 300), ("leaper", "easy", 16, 300),
+    ("chaser", "easy", 16, 300), ("dodgeball", "easy", 16, 300), ("starpilot", "easy", 16, 300),
+]
+
+
+@pytest.mark.parametrize("name,mode,n,steps", OTHER_MODES)
+def test_remaining_distribution_modes_bit_exact(ref_lib, product_lib, name, mode, n, steps):
+    """Every distribution mode each game accepts (game.cpp:56-66) that the main list does not already run."""
+    ref, dut = make_pair(product_lib, n, name, distribution_mode=mode, num_levels=200, start_level=0, rand_seed=0)
+    run_lockstep(ref, dut, steps)
+    ref.close()
+    dut.close()
+
+
+@pytest.mark.parametrize("name,extra", [
+    ("coinrun", dict(restrict_themes=True)),
+    ("coinrun", dict(use_backgrounds=False)),
+    ("heist", dict(center_agent=False)),
+    ("maze", dict(use_sequential_levels=True, num_levels=3)),
+    ("plunder", dict(restrict_themes=True, use_backgrounds=False)),
+    ("coinrun", dict(use_monochrome_assets=True, use_backgrounds=False, restrict_themes=True)),
+    ("chaser", dict(use_monochrome_assets=True, use_backgrounds=False)),
+    ("ninja", dict(paint_vel_info=True)),
+    ("jumper", dict(paint_vel_info=True, use_monochrome_assets=True)),
+    ("fruitbot", dict(use_backgrounds=False, restrict_themes=True)),
+    ("starpilot", dict(use_backgrounds=False)),
+])
+def test_non_default_options_bit_exact(ref_lib, product_lib, name, extra):
+    kw = dict(distribution_mode="hard", num_levels=200, start_level=0, rand_seed=0)
+    kw.update(extra)
+    ref, dut = make_pair(product_lib, 8, name, **kw)
+    run_lockstep(ref, dut, 250)
+    ref.close()
+    dut.close()
+
+
+@pytest.mark.parametrize("name", ["bigfish", "caveflyer", "climber", "dodgeball", "fruitbot", "maze", "miner", "ninja"])
+def test_state_blobs_remaining_games(ref_lib, product_lib, name):
+    """With test_state_blobs_byte_identical_and_portable: all 16 games' wire format on the GPU."""
+    from helpers import run_state_roundtrip
+    from oracle.ref_env import RefVecEnv, default_pack
+
+    kw = dict(distribution_mode="hard", num_levels=200, start_level=0)
+    run_state_roundtrip(lambda seed: RefVecEnv(8, name, rand_seed=seed, **kw),
+                        lambda seed: RefVecEnv(8, name, rand_seed=seed, lib_path=product_lib, resource_root=default_pack(), **kw),
+                        8, 120)
+
+
+@pytest.mark.parametrize("name,mode,n_big,warm,steps", [
+    ("coinrun", "easy", 65536, 40, 200),   # BASELINE configs[1]
+    ("maze", "hard", 32768, 30, 200),      # configs[3]
+    ("bigfish", "hard", 65536, 30, 150),   # configs[2]
+    (ALL16, "hard", 32768, 30, 150),       # configs[4], one GPU's share
+])
+def test_mid_array_envs_match_oracle(ref_lib, product_lib, name, mode, n_big, warm, steps):
+    """Benchmark-size run, envs picked from EVERY launch chunk (not just the first 64): their state is
+    exported through get_state after `warm` steps, loaded into a 64-env oracle, and both are stepped
+    with the same actions — rgb / rew / first every step, state blobs at the end."""
+    import ctypes as C
+
+    import torch
+
+    from oracle.ref_env import MAX_STATE_SIZE, RefVecEnv
+    from procgen_b200 import ProcgenGym3Env
+
+    n_pick = 64
+    n_games = len(name.split(","))
+    rs = np.random.RandomState(11)
+    # pick j of the oracle plays game j % n_games, so the big env index must be congruent to it; one
+    # pick from each of 64 equal slices of the array = every stream chunk is covered several times
+    picks = []
+    for j in range(n_pick):
+        lo, hi = j * (n_big // n_pick), (j + 1) * (n_big // n_pick)
+        e = int(rs.randint(lo, hi))
+        e = e - (e % n_games) + (j % n_games)
+        if e >= hi:
+            e -= n_games
+        picks.append(e)
+    picks = np.array(picks)
+    kw = dict(distribution_mode=mode, num_levels=0, start_level=0)
+    env = ProcgenGym3Env(n_big, name, rand_seed=0, **kw)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.randint(0, 15, (warm + steps, n_big), device="cuda", dtype=torch.int32, generator=gen)
+    for t in range(warm):
+        env.act(acts[t])
+    env.observe()
+    buf = C.create_string_buffer(MAX_STATE_SIZE)
+    ref = RefVecEnv(n_pick, name, rand_seed=99, **kw)
+    for j, e in enumerate(picks):
+        nbytes = int(env._lib.get_state(env._h, int(e), buf, MAX_STATE_SIZE))
+        ref.set_state(j, bytes(buf.raw[:nbytes]))
+    pick_t = torch.as_tensor(picks, device="cuda")
+    r0, o0, f0 = ref.observe()
+    assert np.array_equal(env.observe()[1]["rgb"][pick_t].cpu().numpy(), o0["rgb"]), "frame after set_state"
+    for t in range(warm, warm + steps):
+        env.act(acts[t])
+        ref.act(acts[t][pick_t].cpu().numpy())
+        rew, ob, first = env.observe()
+        r, o, f = ref.observe()
+        assert np.array_equal(rew[pick_t].cpu().numpy(), r), f"step {t}: rew"
+        assert np.array_equal(first[pick_t].cpu().numpy(), f.astype(bool)), f"step {t}: first"
+        d = ob["rgb"][pick_t].cpu().numpy()
+        assert np.array_equal(d, o["rgb"]), f"step {t}: rgb differs for picks {np.nonzero((d != o['rgb']).reshape(n_pick, -1).any(1))[0][:8]}"
+    for j, e in enumerate(picks[::8]):
+        nbytes = int(env._lib.get_state(env._h, int(e), buf, MAX_STATE_SIZE))
+        assert bytes(buf.raw[:nbytes]) == ref.get_state(j * 8), f"state blob of env {e}"
+    assert env.errors() == 0
+    env.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("name", ["bossfight", "caveflyer", "ninja", "starpilot"])
+def test_long_horizon_trig_games(ref_lib, product_lib, name):
+    """10 000 steps (the reference's own state_test horizon, state_test.py:71-124) of the games whose
+    logic calls sin / cos / atan2 / pow: CUDA's double-precision libm is <= 2 ulp against glibc's < 1,
+    so a difference would need a result within ~1e-16 of a rounding boundary — this is the watch for it."""
+    ref, dut = make_pair(product_lib, 8, name, distribution_mode="hard", num_levels=0, start_level=0, rand_seed=3)
+    run_lockstep(ref, dut, 10000, seed=1)
+    ref.close()
+    dut.close()
+
+
+def test_unsnapped_target_rect_bit_exact(ref_lib, product_lib):
+    from helpers import run_snap_off_lockstep
+
+    run_snap_off_lockstep(product_lib)
