@@ -417,6 +417,9 @@ enum ErrBits : uint32_t {
     ERR_SCRATCH_OVERFLOW = 1u << 3,
     ERR_FASSERT = 1u << 4,
     ERR_UNSUPPORTED = 1u << 5,
+    ERR_TILE_ARENA = 1u << 6,   // a frame needed more tiles / general cell blits than its shared-memory arena holds
+    ERR_ENT_BLITS = 1u << 7,    // more visible entity blits than the frame keeps (MAX_VISIBLE_ENTS)
+    ERR_ROT_BLITS = 1u << 8,    // more rotated sprites than the frame keeps (MAX_ROT_BLITS)
 };
 
 }  // namespace pg

@@ -87,6 +87,7 @@ constexpr int CELL_KEY_TYPES = 128;              // grid object ids that can use
 constexpr int CELL_KEYS = CELL_KEY_TYPES * 4;    // x (tw - W0, th - H0) in {0,1}^2
 constexpr uint16_t CELL_GENERAL = 0x8000u;       // cellmap code: 0 none | 1 + texel offset of its tile in the arena | CELL_GENERAL | blit index
 constexpr int MAX_TILE_JOBS = 96;
+constexpr uint32_t BG_NONE = 0xffffffffu;
 
 // colinfo / rowinfo word of a pixel column / row (cells of the visible grid window)
 constexpr uint32_t CI_BASE_MASK = 0x3ffu;        // column: ci * ny; row: cj
@@ -114,12 +115,13 @@ struct FrameT {
     RotBlit *rot;
     RotBlit rot_local[kRotInGlobal ? 1 : kMaxRot];
     // `ents` = VISIBLE entity blits (after culling) in draw order, then the overlay blits (drawn last)
-    static constexpr int kMaxEntBlits = MAX_ENT_BLITS - MAX_OVERLAY_BLITS;
+    static constexpr int kMaxEntBlits = MAX_ENT_BLITS;
+    static constexpr int kMaxList = MAX_ENT_BLITS + MAX_OVERLAY_BLITS;
     Camera cam;
     int32_t low_x, low_y, nx, ny;   // visible grid window: cells [low_x, low_x+nx) x [low_y, low_y+ny)
     int32_t n_bg, n_ent, n_ent_below, n_overlay;  // n_ent_below = entities with render_z == -1
     int32_t snap;
-    int32_t pad;                    // 1: the background is one opaque image covering the device (bgrow[] valid)
+    int32_t pad;                    // 1: the background is one opaque un-mirrored image (bgrow[] valid; it may cover only part of the device)
     int32_t tile_w0, tile_h0;       // smaller of the two snapped cell sizes of this frame
     int32_t n_gen;                  // general cell blits in use
     int32_t tile_top;               // arena words used by tiles
@@ -131,13 +133,13 @@ struct FrameT {
     uint8_t col_p1[MAX_CELLS_1D], col_p2[MAX_CELLS_1D];  // device pixel span [p1,p2) of column i
     uint8_t row_p1[MAX_CELLS_1D], row_p2[MAX_CELLS_1D];
     uint8_t col_tw[MAX_CELLS_1D], row_th[MAX_CELLS_1D];  // snapped size if the column / row can use tiles, else 0
-    static constexpr int kEntWords = (MAX_ENT_BLITS + 63) / 64;
+    static constexpr int kEntWords = (kMaxList + 63) / 64;
     uint64_t ent_rowmask[RES_H][kEntWords];  // bit i: visible entity blit i touches this pixel row
     uint64_t ent_colmask[RES_W][kEntWords];  //        ... this pixel column
     uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
     uint8_t row_lo[RES_H], row_hi[RES_H];
     uint32_t colinfo[RES_W], rowinfo[RES_H];  // CI_* words
-    uint32_t bgrow[RES_H];                    // pad == 1: atlas offset of the background row sampled by pixel row py
+    uint32_t bgrow[RES_H];                    // pad == 1: atlas offset of the background row sampled by pixel row py, BG_NONE outside the image
     uint16_t cellmap[MAX_CELLS_1D * MAX_CELLS_1D];  // [ci * ny + cj], x outer / y inner = draw order
     alignas(4) uint16_t tilekey[MAX_CELLS_1D > 1 ? CELL_KEYS : 4];  // per (type, size variant): 0 unused | 1 wanted | 2 + arena texel offset | 0xffff unavailable
     uint32_t tjob_src[MAX_TILE_JOBS];         // tile copies to stage: texel offset in the table,
@@ -149,7 +151,7 @@ struct FrameT {
     int32_t job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs], job_j0[kMaxTileJobs];
     Blit bg[MAX_BG_BLITS];
     Blit overlay[MAX_OVERLAY_BLITS];
-    Blit ents[MAX_ENT_BLITS];
+    Blit ents[kMaxList];
 
     PG_HD Blit *gen_blit(int k) { return reinterpret_cast<Blit *>(arena + kArenaWords) - 1 - k; }
     PG_HD const Blit *gen_blit(int k) const { return reinterpret_cast<const Blit *>(arena + kArenaWords) - 1 - k; }
@@ -1033,7 +1035,7 @@ struct Raster {
         slot = f.n_rot++;
 #endif
         if (slot >= Frame::kMaxRot) {
-            c.h->err |= ERR_BLIT_OVERFLOW;
+            c.h->err |= ERR_ROT_BLITS;
             return;
         }
         RotBlit &rb = f.rot[slot];
@@ -1191,12 +1193,13 @@ struct Raster {
                 h.err |= ERR_BLIT_OVERFLOW;
             if (h.options.use_backgrounds)
                 G::make_background_blits(c, f);
-            // the usual case — one opaque background image covering the whole device — lets the
-            // shader skip the box test and the blend (Frame::pad = 1)
+            // the usual case — one opaque background image (RGB32: alpha 255) — gets per-row / per-column
+            // source offsets instead of a blit walk (Frame::pad = 1); where the view leaves the
+            // world the image covers only part of the device and the rest stays black
             f.pad = 0;
             if (f.n_bg == 1) {
                 const Blit &b0 = f.bg[0];
-                if (b0.kind == BLIT_IMAGE && b0.x1 == 0 && b0.y1 == 0 && b0.w == RES_W && b0.h == RES_H && b0.opacity == 256 && !b0.mirror)
+                if (b0.kind == BLIT_IMAGE && b0.opacity == 256 && !b0.mirror)
                     f.pad = 1;
             }
             if (h.has_useful_vel_info && h.options.paint_vel_info) {
@@ -1487,7 +1490,7 @@ struct Raster {
                             }
                         }
                     } else {
-                        c.h->err |= ERR_BLIT_OVERFLOW;
+                        c.h->err |= ERR_ENT_BLITS;
                     }
                 }
                 count += total;
@@ -1530,7 +1533,10 @@ struct Raster {
         }
         if (f.pad == 1) {
             const Blit &b = f.bg[0];
-            for (int py = wtid; py < RES_H; py += wn) f.bgrow[py] = b.src + ((b.srcy + (uint32_t)b.iy * (uint32_t)py) >> 16) * b.sw;
+            for (int py = wtid; py < RES_H; py += wn) {
+                const uint32_t dy = (uint32_t)py - b.y1;
+                f.bgrow[py] = dy < b.h ? b.src + ((b.srcy + (uint32_t)b.iy * dy) >> 16) * b.sw : BG_NONE;
+            }
         }
         if (!G::DRAWS_GRID)
             return;
@@ -1648,7 +1654,7 @@ struct Raster {
             slot = f.n_gen++;
 #endif
             if ((slot + 1) * (int)(sizeof(Blit) / 4) + f.tile_top > Frame::kArenaWords) {
-                c.h->err |= ERR_BLIT_OVERFLOW;
+                c.h->err |= ERR_TILE_ARENA;
                 continue;
             }
             const int ci = k / f.ny, cj = k - ci * f.ny;
@@ -1743,6 +1749,16 @@ struct Raster {
         return f.arena[(int)code - 1 + dy * f.col_tw[ci] + dx];
     }
 
+    // pad == 1: source column of the background image for pixel column px (BG_NONE outside), and the texel
+    static PG_HD uint32_t bg_column(const Frame &f, int px) {
+        const Blit &b = f.bg[0];
+        const uint32_t dx = (uint32_t)px - b.x1;
+        return dx < b.w ? (b.basex + (uint32_t)b.ix * dx) >> 16 : BG_NONE;
+    }
+    static PG_HD uint32_t bg_single(const Frame &f, uint32_t bgrow, uint32_t bgcol, const uint32_t *atlas) {
+        return (bgrow != BG_NONE && bgcol != BG_NONE) ? atlas[bgrow + bgcol] : 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
+    }
+
     // Exact bottom-up composition of one pixel in draw order (draw_background, entities z=-1, grid
     // cells x outer / y inner, entities z=0, z=1, overlays; basic-abstract-game.cpp:921-1007). The
     // shader proper (shade_quad) walks the same layers top-down and falls back to this when a
@@ -1750,8 +1766,7 @@ struct Raster {
     static PG_HD_NOINLINE uint32_t shade_exact(const Frame &f, int px, int py, const uint32_t *atlas) {
         uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
         if (f.pad == 1) {
-            const Blit &b = f.bg[0];
-            dst = atlas[f.bgrow[py] + ((b.basex + (uint32_t)b.ix * (uint32_t)px) >> 16)];
+            dst = bg_single(f, f.bgrow[py], bg_column(f, px), atlas);
         } else {
             for (int i = 0; i < f.n_bg; i++) dst = layer_over(dst, blit_texel(f.bg[i], px, py, atlas, f.rot));
         }
@@ -1849,8 +1864,7 @@ struct Raster {
             done = td_entities(f, a, base, px, py, atlas, 0, nb);
         if (!done) {
             if (f.pad == 1) {
-                const Blit &b = f.bg[0];
-                base = atlas[f.bgrow[py] + ((b.basex + (uint32_t)b.ix * (uint32_t)px) >> 16)];  // RGB32 background: alpha 255
+                base = bg_single(f, f.bgrow[py], bg_column(f, px), atlas);  // RGB32 background: alpha 255
             } else {
                 base = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
                 for (int i = f.n_bg - 1; i >= 0; i--)
@@ -1866,7 +1880,7 @@ struct Raster {
     // What a thread keeps for the four pixel columns of its quad while it walks down the rows.
     struct QuadCtx {
         uint32_t ci[4];                    // colinfo
-        uint32_t bg_sx[4];                 // full-screen background: source column per pixel column
+        uint32_t bg_sx[4];                 // single-image background: source column per pixel column (BG_NONE outside)
         uint64_t cm[Frame::kEntWords];     // OR of the four column masks
         int nw;                            // mask words in use this frame
         bool bg_full;
@@ -1876,7 +1890,7 @@ struct Raster {
         q.bg_full = f.pad == 1;
         for (int k = 0; k < 4; k++) {
             q.ci[k] = G::DRAWS_GRID ? f.colinfo[px0 + k] : 0u;
-            q.bg_sx[k] = q.bg_full ? (f.bg[0].basex + (uint32_t)f.bg[0].ix * (uint32_t)(px0 + k)) >> 16 : 0u;
+            q.bg_sx[k] = q.bg_full ? bg_column(f, px0 + k) : 0u;
         }
         for (int w = 0; w < Frame::kEntWords; w++)
             q.cm[w] = w < q.nw ? (f.ent_colmask[px0][w] | f.ent_colmask[px0 + 1][w] | f.ent_colmask[px0 + 2][w] | f.ent_colmask[px0 + 3][w]) : 0;
@@ -1892,7 +1906,7 @@ struct Raster {
             if (w < q.nw)
                 any |= f.ent_rowmask[py][w] & q.cm[w];
         const uint32_t rowinfo = G::DRAWS_GRID ? f.rowinfo[py] : 0u;
-        const uint32_t bgrow = q.bg_full ? f.bgrow[py] : 0u;
+        const uint32_t bgrow = q.bg_full ? f.bgrow[py] : BG_NONE;
         uint32_t c[4];
         for (int k = 0; k < 4; k++) {
             const uint32_t ci = q.ci[k];
@@ -1914,7 +1928,7 @@ struct Raster {
             } else if (s >= 0xff000000u) {
                 c[k] = s;
             } else {
-                const uint32_t bg = atlas[bgrow + q.bg_sx[k]];
+                const uint32_t bg = bg_single(f, bgrow, q.bg_sx[k], atlas);
                 c[k] = s != 0 ? s + pg_byte_mul(bg, (~s) >> 24) : bg;
             }
         }
