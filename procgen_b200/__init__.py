@@ -5,5 +5,8 @@ Importing the package never touches CUDA; constructing an env requires the sm_10
 GPU (there is no CPU fallback).
 """
 from .env import ProcgenGym3Env, BaseProcgenEnv, ENV_NAMES, EXPLORATION_LEVEL_SEEDS, DISTRIBUTION_MODE_DICT  # noqa: F401
+from .wrappers import ProcgenEnv, ToBaselinesVecEnv, ToGymEnv, make, make_env, register_environments  # noqa: F401
 
-__all__ = ["ProcgenGym3Env", "BaseProcgenEnv", "ENV_NAMES"]
+register_environments()  # procgen/__init__.py:10
+
+__all__ = ["ProcgenEnv", "ProcgenGym3Env", "BaseProcgenEnv", "ENV_NAMES", "ToBaselinesVecEnv", "make"]

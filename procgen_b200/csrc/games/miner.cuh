@@ -15,6 +15,7 @@ struct MinerGame : Defaults<MinerGame>, DrawDefaults<MinerGame> {
     static constexpr int SCRATCH_WORDS = 4 * 1280;
     static constexpr int MAX_VISIBLE_ENTS = 64;
     static constexpr int MAX_ROT_BLITS = 0;
+    static constexpr bool ENTS_BELOW_GRID = true;  // the exit sits under the grid layer (render_z = -1, miner.cpp:199)
     static constexpr int MAX_VIEW_CELLS = 20;  // hard: whole 20x20 world; memory mode is centred (11)
     static constexpr const char *NAME = "miner";
     // superset of the types is_blocked and will_reflect accept

@@ -921,6 +921,9 @@ struct Defaults {
     // dodgeball 4.5 -> 3.9 ms, starpilot 1.66 -> 1.36 ms per 32 768 frames, bossfight (all bullets
     // alike) and the games with a rotated sprite or two lose 7-12 %.
     static constexpr bool DEFER_ROTATED = false;
+    // true = the game has entities with render_z == -1 (drawn between the background and the grid
+    // cells, draw_foreground basic-abstract-game.cpp:940): the frame is then composed in three steps
+    static constexpr bool ENTS_BELOW_GRID = false;
     static PG_HD int image_for_type(Ctx &c, int type) { return type < 0 ? -type : type; }
     static PG_HD int theme_for_grid_obj(Ctx &c, int type) { return 0; }
     static PG_HD bool should_draw_entity(Ctx &c, int ei) { return true; }

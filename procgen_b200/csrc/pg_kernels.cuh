@@ -174,7 +174,6 @@ template <class G, class Frame>
 PG_HD void env_render_masks(const KParams &p, int env, Frame &f, int tid, int nthreads) {
     Ctx c = make_ctx(p, env);
     Raster<G, Frame>::frame_cells_finish(c, f, tid, nthreads);
-    Raster<G, Frame>::frame_masks(f, tid, nthreads);
 }
 
 // Host debug harness twin of the bulk copies that stage the frame's tiles
@@ -185,14 +184,10 @@ PG_HD void env_stage_tiles_serial(const KParams &p, Frame &f) {
         for (int w = 0; w < (int)f.tjob_words[j]; w++) f.arena[f.tjob_dst[j] + w] = p.tiles.texels[f.tjob_src[j] + w];
 }
 
-// Shade rows py0, py0 + row_step, ... of the quad column starting at pixel px0 into `out`
-// (packed RGB, 48 words per row). Device: one thread; `out` is the frame's shared-memory copy.
+// Compose the rows row_first, row_first + row_step, ... of the frame (`lane` of `nlanes` threads own them)
 template <class G, class Frame>
-PG_HD void env_render_quad_column(const KParams &p, const Frame &f, int px0, int py0, int row_step, uint32_t *out) {
-    typename Raster<G, Frame>::QuadCtx q;
-    Raster<G, Frame>::quad_begin(f, px0, q);
-    for (int py = py0; py < RES_H; py += row_step)
-        Raster<G, Frame>::shade_quad(f, q, px0, py, p.atlas, out + py * (RES_W * 3 / 4) + (px0 >> 2) * 3);
+PG_HD void env_render_compose(const KParams &p, Frame &f, int row_first, int row_step, int lane, int nlanes) {
+    Raster<G, Frame>::compose_rows(f, f.fb, row_first, row_step, lane, nlanes, p.atlas);
 }
 
 // Fill one tile of the global table (TileTable): tile (slot, tw, th) = the texels an un-clipped

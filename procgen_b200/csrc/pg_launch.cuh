@@ -148,9 +148,10 @@ __device__ __forceinline__ void pg_bulk_store_and_wait(void *dst_gmem, const voi
 // One CTA renders one env's frame:
 //   begin / build / jobs   the blit lists, the cell map and the list of pre-scaled tiles the frame needs
 //   stage                  warp 0 arms the mbarrier and queues one bulk copy per tile (global table -> shared)
-//   masks                  meanwhile: cell codes, row / column masks of the entity blits
-//   shade                  thread = 4 pixel columns x 8 rows, top-down walk per pixel, packed RGB into shared
-//   store                  one bulk copy of the 12 KiB frame to the observation buffer
+//   cells                  meanwhile: the cells learn where their tiles are
+//   compose                warp w owns rows y = w (mod 4): gather (cells over background; a lane = 4 pixel
+//                          columns x 8 rows), then paint the entity blits in draw order, lanes sharing each blit
+//   pack + store           RGB32 -> RGB888 in place, one bulk copy of the 12 KiB frame to the observation buffer
 template <class G>
 __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) render_kernel(KParams p) {
     using Frame = typename FrameFor<G>::type;
@@ -195,12 +196,27 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     PG_RENDER_PHASE(10);
     if (G::DRAWS_GRID)
         pg_mbar_wait(&f.mbar, 0);
-    env_render_quad_column<G, Frame>(p, f, (tid & 15) << 2, tid >> 4, kRenderThreads >> 4, f.out);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of f.out -> visible to the bulk copy
+    // warp w owns rows y = w (mod warps): gather and paint need no block barrier in between
+    env_render_compose<G, Frame>(p, f, tid >> 5, kRenderThreads >> 5, tid & 31, 32);
     __syncthreads();
     PG_RENDER_PHASE(11);
+    {
+        // RGB32 -> RGB888 in place: every thread reads its 8 pixel quads, then (barrier) writes them packed
+        constexpr int kQuadsPerThread = RES_W * RES_H / 4 / kRenderThreads;
+        uint32_t c[kQuadsPerThread][4];
+#pragma unroll
+        for (int j = 0; j < kQuadsPerThread; j++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(f.fb)[tid + j * kRenderThreads];
+            c[j][0] = v.x; c[j][1] = v.y; c[j][2] = v.z; c[j][3] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kQuadsPerThread; j++) Raster<G, Frame>::pack_quad(c[j], f.fb + 3 * (tid + j * kRenderThreads));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of f.fb -> visible to the bulk copy
+    __syncthreads();
     if (tid == 0)
-        pg_bulk_store_and_wait(p.rgb + (size_t)env * (RES_W * RES_H * 3), f.out, RES_W * RES_H * 3);
+        pg_bulk_store_and_wait(p.rgb + (size_t)env * (RES_W * RES_H * 3), f.fb, RES_W * RES_H * 3);
 #undef PG_RENDER_PHASE
 }
 
@@ -228,8 +244,9 @@ void render_env_serial(const KParams &p, int env, Frame &f) {
     env_render_jobs<G, Frame>(p, env, f, 0, 1);
     env_stage_tiles_serial<Frame>(p, f);
     env_render_masks<G, Frame>(p, env, f, 0, 1);
+    for (int w = 0; w < 4; w++) env_render_compose<G, Frame>(p, f, w, 4, 0, 1);  // the device's row ownership, one lane per owner
     uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3));
-    for (int qx = 0; qx < RES_W / 4; qx++) env_render_quad_column<G, Frame>(p, f, qx * 4, 0, 1, out);
+    for (int g = 0; g < RES_W * RES_H / 4; g++) Raster<G, Frame>::pack_quad(f.fb + 4 * g, out + 3 * g);
 }
 
 struct LaunchCtx {

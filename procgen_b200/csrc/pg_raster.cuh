@@ -24,8 +24,8 @@
 //                                  math happens here, once per sprite instead of once per pixel)
 //   frame_tiles      all threads   tiles of tiled entities whose slots frame_build reserved
 //   frame_rots       all threads   (games with DEFER_ROTATED) rotated sprites whose slots were reserved
-//   frame_masks      all threads   per pixel row / column bit masks of the entity blits
-//   shade_pixel      all threads   the gather, one pixel column per thread
+//   frame_tile_alloc / frame_cells_finish   pre-scaled tiles the cells need -> arena + staging jobs
+//   compose_rows     row owners    gather (cells over background) then paint (entity blits in order)
 #pragma once
 #include "pg_engine.cuh"
 
@@ -105,8 +105,9 @@ struct FrameT {
     // slice of a global scratch array instead (L1/L2 resident while the CTA works on the frame).
     static constexpr bool kRotInGlobal = MAX_ROT_BLITS > 32;
     // ---- 16-byte aligned blocks first (bulk-copy targets / sources)
-    // packed RGB frame, assembled here and written out with one bulk store
-    alignas(16) uint32_t out[RES_W * RES_H * 3 / 4];
+    // the frame as 0xFFRRGGBB pixels while it is composed; packed to RGB888 in place (its first
+    // 12 KiB) and written out with one bulk store
+    alignas(16) uint32_t fb[RES_W * RES_H];
     // tiles (texels, growing up from word 0) and general cell blits (32 B each, growing down from the end)
     static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 8;
     alignas(16) uint32_t arena[kArenaWords];
@@ -133,9 +134,6 @@ struct FrameT {
     uint8_t col_p1[MAX_CELLS_1D], col_p2[MAX_CELLS_1D];  // device pixel span [p1,p2) of column i
     uint8_t row_p1[MAX_CELLS_1D], row_p2[MAX_CELLS_1D];
     uint8_t col_tw[MAX_CELLS_1D], row_th[MAX_CELLS_1D];  // snapped size if the column / row can use tiles, else 0
-    static constexpr int kEntWords = (kMaxList + 63) / 64;
-    uint64_t ent_rowmask[RES_H][kEntWords];  // bit i: visible entity blit i touches this pixel row
-    uint64_t ent_colmask[RES_W][kEntWords];  //        ... this pixel column
     uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
     uint8_t row_lo[RES_H], row_hi[RES_H];
     uint32_t colinfo[RES_W], rowinfo[RES_H];  // CI_* words
@@ -1507,6 +1505,8 @@ struct Raster {
         if (below > count)
             below = count;
         if (tid == 0) {
+            if (!G::ENTS_BELOW_GRID && below > 0)
+                c.h->err |= ERR_UNSUPPORTED;  // the game would have to declare ENTS_BELOW_GRID
             f.n_ent = count;
             f.n_ent_below = below;
             if (count > c.h->max_blits_seen)
@@ -1694,35 +1694,9 @@ struct Raster {
         }
     }
 
-    // the overlay blits (drawn after everything else) join the end of the entity list so the
-    // row / column masks cull them like any other blit; one thread, before frame_masks
+    // the overlay blits (drawn after everything else) join the end of the entity list; one thread
     static PG_HD void frame_append_overlays(Frame &f) {
         for (int i = 0; i < f.n_overlay; i++) f.ents[f.n_ent + i] = f.overlay[i];
-    }
-
-    // ---- phase C2: per pixel row / column bit masks of the visible entity blits (+ overlays), so
-    // a pixel only walks the blits whose box really contains it (rowmask & colmask).
-    static PG_HD void frame_masks(Frame &f, int tid, int nthreads) {
-        const int n = f.n_ent + f.n_overlay;
-        for (int t = tid; t < RES_H + RES_W; t += nthreads) {
-            const bool is_row = t < RES_H;
-            const uint32_t q = (uint32_t)(is_row ? t : t - RES_H);
-            uint64_t m[Frame::kEntWords];
-            for (int w = 0; w < Frame::kEntWords; w++) m[w] = 0;
-            for (int i = 0; i < n; i++) {
-                const uint32_t box = *reinterpret_cast<const uint32_t *>(&f.ents[i]);
-                const uint32_t d = is_row ? q - ((box >> 8) & 0xffu) : q - (box & 0xffu);
-                const uint32_t ext = is_row ? (box >> 24) : ((box >> 16) & 0xffu);
-                if (d < ext)
-                    m[i >> 6] |= (uint64_t)1 << (i & 63);
-            }
-            for (int w = 0; w < Frame::kEntWords; w++) {
-                if (is_row)
-                    f.ent_rowmask[q][w] = m[w];
-                else
-                    f.ent_colmask[q][w] = m[w];
-            }
-        }
     }
 
     static PG_HD int ctz64(uint64_t m) {
@@ -1740,7 +1714,15 @@ struct Raster {
 #endif
     }
 
-    // ---- phase D: the gather. Colours are 0xFFRRGGBB (Format_RGB32).
+    // ---- phase D: composition. Colours are 0xFFRRGGBB (Format_RGB32).
+    //   gather   per pixel: the grid cells over the background (draw_background + the cell loop of
+    //            draw_foreground, basic-abstract-game.cpp:921-1007) — the cell under a pixel is a table
+    //            lookup, and an opaque tile texel makes the background fetch unnecessary
+    //   paint    entity blits and overlays in draw order onto the frame (draw_entities z = 0, 1 and
+    //            game_draw overrides): every blit's pixels are spread over the lanes that own its rows
+    // Rows are owned by warps (row y belongs to warp y % 4) in both phases, so a warp-level barrier
+    // is all that separates them; the host debug harness runs the same functions with one "lane".
+
     // source value of cell (ci, cj) at a pixel; `code` = cellmap entry (non-zero)
     static PG_HD uint32_t cell_layer(const Frame &f, uint32_t code, int ci, int cj, int px, int py, const uint32_t *atlas) {
         if (code & CELL_GENERAL)
@@ -1755,164 +1737,63 @@ struct Raster {
         const uint32_t dx = (uint32_t)px - b.x1;
         return dx < b.w ? (b.basex + (uint32_t)b.ix * dx) >> 16 : BG_NONE;
     }
-    static PG_HD uint32_t bg_single(const Frame &f, uint32_t bgrow, uint32_t bgcol, const uint32_t *atlas) {
+    static PG_HD uint32_t bg_single(uint32_t bgrow, uint32_t bgcol, const uint32_t *atlas) {
         return (bgrow != BG_NONE && bgcol != BG_NONE) ? atlas[bgrow + bgcol] : 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
     }
-
-    // Exact bottom-up composition of one pixel in draw order (draw_background, entities z=-1, grid
-    // cells x outer / y inner, entities z=0, z=1, overlays; basic-abstract-game.cpp:921-1007). The
-    // shader proper (shade_quad) walks the same layers top-down and falls back to this when a
-    // pixel stacks more translucent layers than it keeps in registers.
-    static PG_HD_NOINLINE uint32_t shade_exact(const Frame &f, int px, int py, const uint32_t *atlas) {
-        uint32_t dst = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
-        if (f.pad == 1) {
-            dst = bg_single(f, f.bgrow[py], bg_column(f, px), atlas);
-        } else {
-            for (int i = 0; i < f.n_bg; i++) dst = layer_over(dst, blit_texel(f.bg[i], px, py, atlas, f.rot));
-        }
-        const int nb = f.n_ent_below, n = f.n_ent + f.n_overlay;
-        for (int i = 0; i < nb; i++) dst = layer_over(dst, blit_texel(f.ents[i], px, py, atlas, f.rot));
-        if (G::DRAWS_GRID) {
-            const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
-            if (clo != 255 && rlo != 255) {
-                for (int ci = clo; ci <= chi; ci++)
-                    for (int cj = rlo; cj <= rhi; cj++) {
-                        const uint32_t code = f.cellmap[ci * f.ny + cj];
-                        if (code && px >= f.col_p1[ci] && px < f.col_p2[ci] && py >= f.row_p1[cj] && py < f.row_p2[cj])
-                            dst = layer_over(dst, cell_layer(f, code, ci, cj, px, py, atlas));
-                    }
-            }
-        }
-        for (int i = nb; i < n; i++) dst = layer_over(dst, blit_texel(f.ents[i], px, py, atlas, f.rot));
+    // draw_background at one pixel, any number of background blits (tiled backgrounds), bottom-up
+    static PG_HD_NOINLINE uint32_t bg_generic(const Frame &f, int px, int py, const uint32_t *atlas) {
+        uint32_t dst = 0xff000000u;
+        if (f.pad == 1)
+            return bg_single(f.bgrow[py], bg_column(f, px), atlas);
+        for (int i = 0; i < f.n_bg; i++) dst = layer_over(dst, blit_texel(f.bg[i], px, py, atlas, f.rot));
         return dst;
     }
 
-    // translucent layers met on the way down, deepest first after the walk (p0 = last pushed)
-    struct Partials {
-        uint32_t p0, p1, p2, p3;
-        bool overflow;
-    };
-    // returns true when the layer is opaque: the walk ends, `base` is the colour to blend onto
-    static PG_HD bool td_layer(Partials &a, uint32_t s, uint32_t &base) {
-        if (s >= 0xff000000u) {
-            base = s;
-            return true;
+    // all cells over `under` at one pixel, in draw order (x outer / y inner): the out-of-line path
+    // for pixels where neighbouring cells overlap or a cell is a general blit
+    static PG_HD_NOINLINE uint32_t cells_generic(const Frame &f, int px, int py, const uint32_t *atlas, uint32_t under) {
+        uint32_t dst = under;
+        const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
+        if (clo != 255 && rlo != 255) {
+            for (int ci = clo; ci <= chi; ci++)
+                for (int cj = rlo; cj <= rhi; cj++) {
+                    const uint32_t code = f.cellmap[ci * f.ny + cj];
+                    if (code && px >= f.col_p1[ci] && px < f.col_p2[ci] && py >= f.row_p1[cj] && py < f.row_p2[cj])
+                        dst = layer_over(dst, cell_layer(f, code, ci, cj, px, py, atlas));
+                }
         }
-        if (s != 0) {
-            if (a.p3 != 0)
-                a.overflow = true;
-            a.p3 = a.p2;
-            a.p2 = a.p1;
-            a.p1 = a.p0;
-            a.p0 = s;
-        }
-        return false;
-    }
-    static PG_HD uint32_t td_resolve(const Partials &a, uint32_t base) {
-        if (a.p0 != 0) base = a.p0 + pg_byte_mul(base, (~a.p0) >> 24);
-        if (a.p1 != 0) base = a.p1 + pg_byte_mul(base, (~a.p1) >> 24);
-        if (a.p2 != 0) base = a.p2 + pg_byte_mul(base, (~a.p2) >> 24);
-        if (a.p3 != 0) base = a.p3 + pg_byte_mul(base, (~a.p3) >> 24);
-        return base;
-    }
-
-    // entity / overlay blits [lo_bit, hi_bit) whose row and column masks contain the pixel, topmost first
-    static PG_HD bool td_entities(const Frame &f, Partials &a, uint32_t &base, int px, int py, const uint32_t *atlas, int lo_bit, int hi_bit) {
-        for (int w = (hi_bit - 1) >> 6; w >= (lo_bit >> 6); w--) {
-            uint64_t mw = f.ent_rowmask[py][w] & f.ent_colmask[px][w];
-            if (mw == 0)
-                continue;
-            const int lo = lo_bit - w * 64, hi = hi_bit - w * 64;
-            if (lo > 0)
-                mw &= ~(((uint64_t)1 << lo) - 1);
-            if (hi < 64)
-                mw &= ((uint64_t)1 << hi) - 1;
-            while (mw) {
-                const int i = top_bit64(mw);
-                mw &= ~((uint64_t)1 << i);
-                if (td_layer(a, blit_texel(f.ents[w * 64 + i], px, py, atlas, f.rot), base))
-                    return true;
-            }
-        }
-        return false;
-    }
-
-    // One pixel, every layer, top-down: overlays and entities above the grid, grid cells (last drawn
-    // first), entities below, background. Out of line: the shader proper (shade_quad) only calls it
-    // for pixels that have more than "at most one tile cell over a full-screen background".
-    static PG_HD_NOINLINE uint32_t shade_generic(const Frame &f, int px, int py, const uint32_t *atlas) {
-        Partials a;
-        a.p0 = a.p1 = a.p2 = a.p3 = 0;
-        a.overflow = false;
-        uint32_t base = 0;
-        const int nb = f.n_ent_below, n_all = f.n_ent + f.n_overlay;
-        bool done = false;
-        if (n_all > nb)
-            done = td_entities(f, a, base, px, py, atlas, nb, n_all);
-        if (G::DRAWS_GRID && !done) {
-            const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
-            if (clo != 255 && rlo != 255) {
-                for (int cc = chi; cc >= clo && !done; cc--)
-                    for (int cj = rhi; cj >= rlo && !done; cj--) {
-                        const uint32_t code = f.cellmap[cc * f.ny + cj];
-                        if (code && px >= f.col_p1[cc] && px < f.col_p2[cc] && py >= f.row_p1[cj] && py < f.row_p2[cj])
-                            done = td_layer(a, cell_layer(f, code, cc, cj, px, py, atlas), base);
-                    }
-            }
-        }
-        if (!done && nb > 0)
-            done = td_entities(f, a, base, px, py, atlas, 0, nb);
-        if (!done) {
-            if (f.pad == 1) {
-                base = bg_single(f, f.bgrow[py], bg_column(f, px), atlas);  // RGB32 background: alpha 255
-            } else {
-                base = 0xff000000u;  // fillRect(rect, black), basic-abstract-game.cpp:980
-                for (int i = f.n_bg - 1; i >= 0; i--)
-                    if (td_layer(a, blit_texel(f.bg[i], px, py, atlas, f.rot), base))
-                        break;
-            }
-        }
-        if (a.overflow)
-            return shade_exact(f, px, py, atlas);
-        return td_resolve(a, base);
+        return dst;
     }
 
     // What a thread keeps for the four pixel columns of its quad while it walks down the rows.
     struct QuadCtx {
         uint32_t ci[4];                    // colinfo
         uint32_t bg_sx[4];                 // single-image background: source column per pixel column (BG_NONE outside)
-        uint64_t cm[Frame::kEntWords];     // OR of the four column masks
-        int nw;                            // mask words in use this frame
-        bool bg_full;
+        bool bg_one;
     };
     static PG_HD void quad_begin(const Frame &f, int px0, QuadCtx &q) {
-        q.nw = (f.n_ent + f.n_overlay + 63) >> 6;
-        q.bg_full = f.pad == 1;
+        q.bg_one = f.pad == 1;
         for (int k = 0; k < 4; k++) {
             q.ci[k] = G::DRAWS_GRID ? f.colinfo[px0 + k] : 0u;
-            q.bg_sx[k] = q.bg_full ? bg_column(f, px0 + k) : 0u;
+            q.bg_sx[k] = q.bg_one ? bg_column(f, px0 + k) : 0u;
         }
-        for (int w = 0; w < Frame::kEntWords; w++)
-            q.cm[w] = w < q.nw ? (f.ent_colmask[px0][w] | f.ent_colmask[px0 + 1][w] | f.ent_colmask[px0 + 2][w] | f.ent_colmask[px0 + 3][w]) : 0;
     }
 
-    // Four horizontally adjacent pixels of row py -> 12 packed RGB bytes (3 words) at out[0..2]:
-    // bgr32_to_rgb888 (game.cpp:8-23) fused into the shader. The inline part covers the common
-    // pixel — no entity blit near, at most one cell and that one from a pre-scaled tile, full-screen
-    // background: tile texel first, background fetched only when the texel is not opaque.
-    static PG_HD void shade_quad(const Frame &f, const QuadCtx &q, int px0, int py, const uint32_t *atlas, uint32_t *out) {
-        uint64_t any = 0;
-        for (int w = 0; w < Frame::kEntWords; w++)
-            if (w < q.nw)
-                any |= f.ent_rowmask[py][w] & q.cm[w];
-        const uint32_t rowinfo = G::DRAWS_GRID ? f.rowinfo[py] : 0u;
-        const uint32_t bgrow = q.bg_full ? f.bgrow[py] : BG_NONE;
-        uint32_t c[4];
+    enum GatherMode { GATHER_ALL = 0, GATHER_BG = 1, GATHER_CELLS = 2 };  // background + cells | background only | cells over what fb holds
+
+    // Four horizontally adjacent pixels of row py -> fb. The inline part covers the common pixel —
+    // at most one cell and that one from a pre-scaled tile: tile texel first, the background (or
+    // what is already in fb) only when the texel is not opaque.
+    template <int MODE>
+    static PG_HD void gather_quad(const Frame &f, const QuadCtx &q, int px0, int py, const uint32_t *atlas, uint32_t *fb) {
+        const uint32_t rowinfo = (G::DRAWS_GRID && MODE != GATHER_BG) ? f.rowinfo[py] : 0u;
+        const uint32_t bgrow = q.bg_one ? f.bgrow[py] : BG_NONE;
+        uint32_t *dst = fb + py * RES_W + px0;
         for (int k = 0; k < 4; k++) {
             const uint32_t ci = q.ci[k];
-            bool slow = any != 0 || !q.bg_full;
             uint32_t s = 0;
-            if (G::DRAWS_GRID && !slow && (ci & rowinfo & CI_VALID)) {
+            bool slow = false;
+            if (G::DRAWS_GRID && MODE != GATHER_BG && (ci & rowinfo & CI_VALID)) {
                 if ((ci | rowinfo) & CI_MULTI) {
                     slow = true;
                 } else {
@@ -1923,16 +1804,64 @@ struct Raster {
                         s = f.arena[(int)code - 1 + (int)((rowinfo >> CI_D_SHIFT) & 31u) * (int)((ci >> CI_TW_SHIFT) & 31u) + (int)((ci >> CI_D_SHIFT) & 31u)];
                 }
             }
-            if (slow) {
-                c[k] = shade_generic(f, px0 + k, py, atlas);
-            } else if (s >= 0xff000000u) {
-                c[k] = s;
-            } else {
-                const uint32_t bg = bg_single(f, bgrow, q.bg_sx[k], atlas);
-                c[k] = s != 0 ? s + pg_byte_mul(bg, (~s) >> 24) : bg;
+            if (s >= 0xff000000u && !slow) {
+                dst[k] = s;
+                continue;
             }
+            uint32_t under;
+            if (MODE == GATHER_CELLS)
+                under = dst[k];
+            else if (q.bg_one)
+                under = bg_single(bgrow, q.bg_sx[k], atlas);
+            else
+                under = bg_generic(f, px0 + k, py, atlas);
+            if (slow)
+                dst[k] = cells_generic(f, px0 + k, py, atlas, under);
+            else
+                dst[k] = s != 0 ? s + pg_byte_mul(under, (~s) >> 24) : under;
         }
-        // 0xAARRGGBB -> bytes R,G,B
+    }
+
+    // Paint blits [lo, hi) of the entity list, in list order, onto the rows row_first, row_first +
+    // row_step, ... of fb. The `nlanes` threads that share those rows split every blit's pixels.
+    static PG_HD void paint_blits(const Frame &f, uint32_t *fb, int lo, int hi, int row_first, int row_step, int lane, int nlanes, const uint32_t *atlas) {
+        for (int i = lo; i < hi; i++) {
+            const Blit &b = f.ents[i];
+            const uint32_t box = *reinterpret_cast<const uint32_t *>(&b);  // x1 | y1<<8 | w<<16 | h<<24
+            const int x1 = (int)(box & 0xffu), y1 = (int)((box >> 8) & 0xffu), w = (int)((box >> 16) & 0xffu), h = (int)(box >> 24);
+            if (w == 0)
+                continue;
+            int r0 = (row_first - y1) % row_step;  // first row of the box that is ours
+            if (r0 < 0)
+                r0 += row_step;
+            const int nrows = r0 < h ? (h - 1 - r0) / row_step + 1 : 0;
+            const int n = nrows * w;
+            const bool plain = b.kind == BLIT_IMAGE;
+            for (int idx = lane; idx < n; idx += nlanes) {
+                const int r = idx / w, dx = idx - r * w, dy = r0 + r * row_step;
+                uint32_t s;
+                if (plain) {
+                    uint32_t sx = (b.basex + (uint32_t)b.ix * (uint32_t)dx) >> 16;
+                    const uint32_t sy = (b.srcy + (uint32_t)b.iy * (uint32_t)dy) >> 16;
+                    if (b.mirror)
+                        sx = b.sw - 1 - sx;
+                    s = layer_of(atlas[b.src + sy * b.sw + sx], b.opacity);
+                } else {
+                    s = blit_texel(b, x1 + dx, y1 + dy, atlas, f.rot);
+                }
+                if (s != 0) {
+                    uint32_t *px = fb + (y1 + dy) * RES_W + x1 + dx;
+                    *px = layer_over(*px, s);
+                }
+            }
+#if defined(__CUDA_ARCH__)
+            __syncwarp();  // the next blit may overlap this one
+#endif
+        }
+    }
+
+    // 0xFFRRGGBB x 4 -> 12 packed RGB bytes (3 words): bgr32_to_rgb888 (game.cpp:8-23)
+    static PG_HD void pack_quad(const uint32_t *c, uint32_t *out) {
 #if defined(__CUDA_ARCH__)
         out[0] = __byte_perm(c[0], c[1], 0x6012);
         out[1] = __byte_perm(c[1], c[2], 0x5601);
@@ -1946,6 +1875,41 @@ struct Raster {
         out[1] = g1 | (b1 << 8) | (r2 << 16) | (g2 << 24);
         out[2] = b2 | (r3 << 8) | (g3 << 16) | (b3 << 24);
 #endif
+    }
+
+    // Everything the owner of rows row_first, row_first + row_step, ... does to them: `lane` of
+    // `nlanes` threads (a warp on the device; 16 quad columns x 2 interleaved row sets per lane pair)
+    static PG_HD void compose_rows(const Frame &f, uint32_t *fb, int row_first, int row_step, int lane, int nlanes, const uint32_t *atlas) {
+        const int nb = f.n_ent_below, n_all = f.n_ent + f.n_overlay;
+        // lanes tile the rows: quad column = lane % 16, and lane / 16 picks every (nlanes / 16)-th of our rows
+        const int per_row = RES_W / 4;
+        const int sub = nlanes >= per_row ? nlanes / per_row : 1;
+        for (int qx = lane % per_row; qx < per_row; qx += (nlanes < per_row ? nlanes : per_row)) {
+            QuadCtx q;
+            quad_begin(f, qx * 4, q);
+            const int first = row_first + row_step * (nlanes >= per_row ? lane / per_row : 0);
+            if (G::ENTS_BELOW_GRID && nb > 0) {
+                for (int py = first; py < RES_H; py += row_step * sub) gather_quad<GATHER_BG>(f, q, qx * 4, py, atlas, fb);
+            } else {
+                for (int py = first; py < RES_H; py += row_step * sub) gather_quad<GATHER_ALL>(f, q, qx * 4, py, atlas, fb);
+            }
+        }
+        if (G::ENTS_BELOW_GRID && nb > 0) {
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+            paint_blits(f, fb, 0, nb, row_first, row_step, lane, nlanes, atlas);
+            for (int qx = lane % per_row; qx < per_row; qx += (nlanes < per_row ? nlanes : per_row)) {
+                QuadCtx q;
+                quad_begin(f, qx * 4, q);
+                const int first = row_first + row_step * (nlanes >= per_row ? lane / per_row : 0);
+                for (int py = first; py < RES_H; py += row_step * sub) gather_quad<GATHER_CELLS>(f, q, qx * 4, py, atlas, fb);
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        paint_blits(f, fb, (G::ENTS_BELOW_GRID ? nb : 0), n_all, row_first, row_step, lane, nlanes, atlas);
     }
 };
 
