@@ -282,6 +282,8 @@ def run_ours(args):
 
     env = ProcgenGym3Env(n, args.game, distribution_mode=args.mode, num_levels=0, start_level=0, rand_seed=0,
                          shard=(rank, world) if world > 1 else None)
+    if args.gather and dist is not None and not args.nccl_gather:
+        env.enable_peer_gather(0)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     T = 256
     actions = torch.randint(0, 15, (T, n), device=dev, dtype=torch.int32, generator=gen)
@@ -382,6 +384,8 @@ def run_ours(args):
                                "desync steps", "steps": K5,
                    "value": n5 * world * K5 / (ms_plain / 1000.0), "ms_per_step": ms_plain / K5, "unit": "env-steps/s"}
         if dist is not None:
+            if not args.nccl_gather:
+                env5.enable_peer_gather(0)
             for t in range(2):
                 env5.act(act5[t])
                 env5.observe()
@@ -478,6 +482,7 @@ def main():
     ap.add_argument("--config5", action="store_true", help="also measure BASELINE configs[4] (16-game list, 32768 envs/GPU)")
     ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--config5-desync", type=int, default=300)
+    ap.add_argument("--nccl-gather", action="store_true", help="keep the plain NCCL gather (no peer writes) for the gather measurements")
     ap.add_argument("--gather", action="store_true",
                     help="BASELINE configs[4] variant: NCCL-gather every step's rgb shard to rank 0 inside the timed region")
     args = ap.parse_args()

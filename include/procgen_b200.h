@@ -184,6 +184,16 @@ LIBENV_API int pgb200_debug_cycles(libenv_env *handle, uint32_t *host_out);
  * max_ents entity records (128 B each, csrc/pg_state.cuh Entity) to host memory; returns n_ents. */
 LIBENV_API int pgb200_debug_read_env(libenv_env *handle, int env, void *hdr_out, void *ents_out, int max_ents);
 
+/* Peer mirror for the single gather of a sharded run (BASELINE configs[4]): mirror0 / mirror1
+ * are device-accessible addresses (typically another GPU's memory mapped over NVLink: CUDA IPC or
+ * torch symmetric memory) of this shard's [num_envs][64][64][3] slot in the gathered array. Every
+ * step then copies each launch's frames there right behind its render kernel, alternating between
+ * the two buffers step by step (pgb200_mirror_parity = the buffer the latest step wrote). Passing
+ * NULL switches it off. The caller owns the synchronisation between ranks. Returns 0, or -1 in the
+ * host debug build. */
+LIBENV_API int pgb200_set_rgb_mirror(libenv_env *handle, void *mirror0, void *mirror1);
+LIBENV_API int pgb200_mirror_parity(libenv_env *handle);
+
 /* Introspection: shared memory of one render CTA (the per-game frame) and the number of render CTAs
  * per SM the render kernel of `game` is compiled for. Returns -1 for an unknown game. */
 LIBENV_API int pgb200_frame_info(const char *game, int *frame_bytes, int *ctas_per_sm);

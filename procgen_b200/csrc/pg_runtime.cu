@@ -237,6 +237,10 @@ struct VecEnv {
     int max_logic_blocks = 1 << 30;
     int render_smem_floor = 0;
     // host-buffer (libenv) mode
+    // peer mirror (config 5): when set, every launch's frames are also copied into
+    // these buffers (another GPU's memory, mapped through NVLink) right behind its render kernel
+    uint8_t *mirror[2] = {nullptr, nullptr};
+    int mirror_parity = 0;
     bool have_host_bufs = false;
     bool rgb_copy_enqueued = false;  // this step's observation DMA already follows the render kernels
     bool ob_direct = false;      // caller's obs block is contiguous and page-locked: DMA straight into it
@@ -292,6 +296,8 @@ struct VecEnv {
             }
         }
 #endif
+        if (!init && mirror[0])
+            mirror_parity ^= 1;
         int k = 0;
         for (int g = 0; g < G; g++) {
             for (int cidx = 0; cidx < chunks; cidx++, k++) {
@@ -329,6 +335,18 @@ struct VecEnv {
                 // render kernel, on the same stream, so the copy of one chunk overlaps the kernels
                 // of the next instead of waiting for the whole step (PCIe is the e2e bottleneck:
                 // 12 KiB per env and step)
+                if (!init && mirror[0] && hi > lo) {
+                    // the gather of SURVEY §8e without a collective: this launch's frames go straight
+                    // to their place in the destination rank's buffer, overlapping the other launches
+                    const size_t frame = RES_W * RES_H * 3;
+                    const size_t first = (size_t)(g + lo * G) * frame;
+                    if (G == 1)
+                        CUDA_CHECK(cudaMemcpyAsync(mirror[mirror_parity] + first, base.rgb + first, (size_t)(hi - lo) * frame,
+                                                   cudaMemcpyDeviceToDevice, lc.stream));
+                    else
+                        CUDA_CHECK(cudaMemcpy2DAsync(mirror[mirror_parity] + first, (size_t)G * frame, base.rgb + first, (size_t)G * frame, frame,
+                                                     (size_t)(hi - lo), cudaMemcpyDeviceToDevice, lc.stream));
+                }
                 if (have_host_bufs && G == 1 && hi > lo) {
                     const size_t frame = RES_W * RES_H * 3;
                     uint8_t *rgb_dst = ob_direct ? (uint8_t *)h_ob[0] : st_rgb;
@@ -940,6 +958,23 @@ void pgb200_set_stream(libenv_env *handle, void *stream) {
     (void)stream;
 #endif
 }
+
+int pgb200_set_rgb_mirror(libenv_env *handle, void *mirror0, void *mirror1) {
+#ifndef PG_HOSTSIM
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->sync();
+    v->mirror[0] = (uint8_t *)mirror0;
+    v->mirror[1] = (uint8_t *)(mirror1 ? mirror1 : mirror0);
+    v->mirror_parity = 0;
+    return 0;
+#else
+    (void)handle; (void)mirror0; (void)mirror1;
+    return -1;
+#endif
+}
+
+int pgb200_mirror_parity(libenv_env *handle) { return ((VecEnv *)handle)->mirror_parity; }
 
 void pgb200_act_device(libenv_env *handle) {
     VecEnv *v = (VecEnv *)handle;

@@ -342,13 +342,55 @@ class BaseProcgenEnv:
         pairs = int(self._lib.pgb200_kernel_timing_end(self._h, out))
         return {"logic_ms": out[0], "render_ms": out[1], "launch_pairs": pairs, "env_steps": out[3]}
 
+    def enable_peer_gather(self, dst: int = 0) -> bool:
+        """Turn gather_observations() into peer writes: allocate the gathered array as torch symmetric
+        memory (every rank maps every rank's copy over NVLink), hand the library the address of this
+        shard's slot in `dst`'s copy, and let every render launch be followed by a copy of its frames
+        to that slot (pgb200_set_rgb_mirror) — the transfer then overlaps the rest of the step and
+        gather_observations() only has to run one cross-rank barrier. Collective (call on all ranks).
+        Returns False (and keeps the NCCL gather) when symmetric memory cannot be set up."""
+        import torch.distributed as dist
+
+        torch = self._torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ok = torch.zeros(1, device=self._dev, dtype=torch.int32)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            n = self.num
+            frame = 64 * 64 * 3
+            buf = symm_mem.empty((2 * world * n * frame,), dtype=torch.uint8, device=self._dev)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            ptr = int(hdl.buffer_ptrs[dst])
+            slots = [ptr + (b * world * n + rank * n) * frame for b in (0, 1)]
+            self._peer = {"buf": buf, "hdl": hdl, "dst": dst, "slots": slots,
+                          "views": [buf[b * world * n * frame:(b + 1) * world * n * frame].view(world * n, 64, 64, 3) for b in (0, 1)]}
+            ok += 1
+        except Exception as e:  # noqa: BLE001 - any failure means: keep the collective
+            self._peer_error = repr(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) != 1:
+            self._peer = None
+            return False
+        with torch.cuda.device(self._dev):
+            self._lib.pgb200_set_rgb_mirror(self._h, C.c_void_p(self._peer["slots"][0]), C.c_void_p(self._peer["slots"][1]))
+        return True
+
     def gather_observations(self, dst: int = 0):
-        """The only collective on this path: NCCL gather of this rank's rgb shard to `dst`.
-        Returns u8[world*num,64,64,3] on dst, None elsewhere."""
+        """The only cross-rank exchange on this path: every rank's rgb shard on `dst`.
+        Returns u8[world*num,64,64,3] on dst, None elsewhere. After enable_peer_gather() the frames
+        were already written into dst's memory behind each render launch and this is one barrier;
+        otherwise it is one NCCL gather."""
         import torch.distributed as dist
 
         torch = self._torch
         world = dist.get_world_size()
+        peer = getattr(self, "_peer", None)
+        if peer is not None and peer["dst"] == dst:
+            peer["hdl"].barrier(channel=0)   # on the current stream: every rank's copies of this step have landed
+            if dist.get_rank() == dst:
+                return peer["views"][int(self._lib.pgb200_mirror_parity(self._h))]
+            return None
         if dist.get_rank() == dst:
             out = getattr(self, "_gather_buf", None)
             if out is None or out.shape[0] != world * self.num:
@@ -359,9 +401,16 @@ class BaseProcgenEnv:
         return None
 
     def gather_how(self) -> str:
-        return "torch.distributed.gather (NCCL) of the rgb shard after the step"
+        if getattr(self, "_peer", None) is not None:
+            return ("peer writes: each render launch is followed by a copy of its frames into rank-0 symmetric memory over "
+                    "NVLink (pgb200_set_rgb_mirror); gather = one symmetric-memory barrier per step")
+        return "torch.distributed.gather (NCCL) of the rgb shard after the step" + (
+            f" (peer path unavailable: {self._peer_error})" if getattr(self, "_peer_error", None) else "")
 
     def close(self):
+        if getattr(self, "_peer", None) is not None and getattr(self, "_h", None):
+            self._lib.pgb200_set_rgb_mirror(self._h, None, None)
+            self._peer = None
         if getattr(self, "_h", None):
             self._lib.libenv_close(self._h)
             self._h = None

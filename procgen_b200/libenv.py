@@ -48,7 +48,7 @@ EXPORTS = ["libenv_version", "libenv_make", "libenv_get_tensortypes", "libenv_se
            "libenv_act", "libenv_close", "pgb200_get_device_buffers", "pgb200_set_stream", "pgb200_act_device",
            "pgb200_sync", "pgb200_get_errors", "pgb200_debug_cycles", "pgb200_debug_read_env", "pgb200_kernel_launches", "pgb200_is_device_build",
            "pgb200_kernel_timing_begin", "pgb200_kernel_timing_end", "get_state", "set_state", "pgb200_set_launch_shape",
-           "pgb200_frame_info"]
+           "pgb200_frame_info", "pgb200_set_rgb_mirror", "pgb200_mirror_parity"]
 
 _lib = None
 
@@ -76,6 +76,10 @@ def bind(lib):
     lib.pgb200_debug_read_env.restype = C.c_int
     lib.pgb200_frame_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pgb200_frame_info.restype = C.c_int
+    lib.pgb200_set_rgb_mirror.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pgb200_set_rgb_mirror.restype = C.c_int
+    lib.pgb200_mirror_parity.argtypes = [C.c_void_p]
+    lib.pgb200_mirror_parity.restype = C.c_int
     lib.pgb200_kernel_launches.argtypes = [C.c_void_p]
     lib.pgb200_kernel_launches.restype = C.c_int64
     lib.get_state.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]

@@ -302,3 +302,42 @@ def test_unsnapped_target_rect_bit_exact(ref_lib, product_lib):
     from helpers import run_snap_off_lockstep
 
     run_snap_off_lockstep(product_lib)
+
+
+def test_baselines_vecenv_and_gym_wrappers(ref_lib, product_lib):
+    """ProcgenEnv / ToBaselinesVecEnv (env.py:249-265) and the procgen-<name>-v0 gym interface
+    (gym_registration.py:6-34): same reset/step protocol, same numbers as the oracle."""
+    from oracle.ref_env import RefVecEnv, mt19937_actions
+    import procgen_b200
+
+    kw = dict(distribution_mode="easy", num_levels=50, start_level=0, rand_seed=4)
+    venv = procgen_b200.ProcgenEnv(num_envs=8, env_name="coinrun", **kw)
+    ref = RefVecEnv(8, "coinrun", **kw)
+    assert venv.num_envs == 8 and venv.observation_space["rgb"].shape == (64, 64, 3) and venv.action_space.n == 15
+    ob = venv.reset()
+    assert np.array_equal(ob["rgb"], ref.observe()[1]["rgb"])
+    acts = mt19937_actions(2, 8, 150)
+    for t in range(150):
+        ob, rew, done, infos = venv.step(acts[t])
+        ref.act(acts[t])
+        r, o, f = ref.observe()
+        assert np.array_equal(ob["rgb"], o["rgb"]) and np.array_equal(rew, r) and np.array_equal(done, f.astype(bool))
+        assert [i["level_seed"] for i in infos] == list(ref.info["level_seed"])
+        assert [i["prev_level_complete"] for i in infos] == list(ref.info["prev_level_complete"])
+    assert venv.render(mode="rgb_array").shape == (64, 64, 3)
+    venv.close()
+    ref.close()
+
+    genv = procgen_b200.make("procgen-maze-v0", distribution_mode="easy", num_levels=20, start_level=0, rand_seed=1)
+    ref = RefVecEnv(1, "maze", distribution_mode="easy", num_levels=20, start_level=0, rand_seed=1)
+    ob = genv.reset()
+    assert ob.shape == (64, 64, 3) and np.array_equal(ob, ref.observe()[1]["rgb"][0])
+    acts = mt19937_actions(9, 1, 200)
+    for t in range(200):
+        ob, rew, done, info = genv.step(int(acts[t][0]))
+        ref.act(acts[t])
+        r, o, f = ref.observe()
+        assert np.array_equal(ob, o["rgb"][0]) and rew == float(r[0]) and done == bool(f[0])
+        assert info["level_seed"] == int(ref.info["level_seed"][0])
+    genv.close()
+    ref.close()
