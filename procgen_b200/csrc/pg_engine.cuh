@@ -785,7 +785,10 @@ struct Engine {
         h.action = h.default_action;
     }
 
-    static PG_HD void step(Ctx &c) {
+    // Game::step (game.cpp:120-155) in two halves, so that the vector runtime can run level generation
+    // (the reset of an episode that just ended) as a separate pass: step_play = everything up to the
+    // decision `if (step_data.done) reset()`, returns that decision; step_finish = the rest.
+    static PG_HD bool step_play(Ctx &c) {
         EnvHdr &h = *c.h;
         h.cur_time += 1;
         bool will_force_reset = false;
@@ -804,12 +807,17 @@ struct Engine {
             h.last_reward = h.reward;
         }
         h.prev_level_seed = h.current_level_seed;
-        if (h.done)
+        return h.done != 0;
+    }
+    static PG_HD void step_finish(Ctx &c, bool do_reset) {
+        EnvHdr &h = *c.h;
+        if (do_reset)
             reset(c);
         if (h.options.use_sequential_levels && h.level_complete)
             h.done = 0;
         h.episode_done = h.done;
     }
+    static PG_HD void step(Ctx &c) { step_finish(c, step_play(c)); }
 };
 
 // ---------------------------------------------------------------- default hooks (the virtuals)

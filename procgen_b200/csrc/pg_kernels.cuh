@@ -41,8 +41,16 @@ struct KParams {
     int32_t fixed_asset_seed;   // FNV-1a of the game name (vecgame.cpp:156-167, 324-327)
     int32_t snap;
     int32_t env_global_offset;  // game_n = env_global_offset + env
+    // level generation as its own pass (see pg_launch.cuh): envs whose episode ended this step
+    int32_t *reset_list;        // this launch's segment: env indices, filled by the logic kernel
+    unsigned int *reset_count;  // entries in reset_list (null: resets run inline in the logic kernel)
+    int32_t *reset_epoch;       // [N] step id at which the env last entered a reset list
+    int32_t step_id;
+    int32_t render_mode;        // RENDER_ALL | RENDER_SKIP_RESET (envs listed this step are left to the tail launch) | RENDER_LISTED
     uint32_t *dbg_cycles;       // optional [N] per-env logic duration in SM cycles (profiling aid)
 };
+
+enum RenderMode : int32_t { RENDER_ALL = 0, RENDER_SKIP_RESET = 1, RENDER_LISTED = 2 };
 
 PG_HD Ctx make_ctx(const KParams &p, int env) {
     Ctx c;
@@ -139,7 +147,31 @@ PG_HD void env_step_logic(const KParams &p, int env) {
 #endif
     Ctx c = make_ctx(p, env);
     c.h->action = p.action[env];  // vecgame.cpp:388
-    Engine<G>::step(c);
+    const bool ended = Engine<G>::step_play(c);
+    if (ended && p.reset_count != nullptr) {
+        // level generation runs in the reset pass; it also finishes the step there
+#if defined(__CUDA_ARCH__)
+        if ((threadIdx.x & 31u) == 0) {
+            const unsigned slot = atomicAdd(p.reset_count, 1u);
+            p.reset_list[slot] = env;
+            p.reset_epoch[env] = p.step_id;
+        }
+#else
+        p.reset_list[(*p.reset_count)++] = env;
+        p.reset_epoch[env] = p.step_id;
+#endif
+        return;
+    }
+    Engine<G>::step_finish(c, ended);
+    Raster<G, Frame>::prepare_camera(c);
+    write_step_outputs(p, env, *c.h);
+}
+
+// the second half of Game::step for an env whose episode ended: reset() = level generation
+template <class G, class Frame>
+PG_HD void env_reset_logic(const KParams &p, int env) {
+    Ctx c = make_ctx(p, env);
+    Engine<G>::step_finish(c, true);
     Raster<G, Frame>::prepare_camera(c);
     write_step_outputs(p, env, *c.h);
 }

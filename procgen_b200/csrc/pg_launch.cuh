@@ -92,6 +92,31 @@ __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kern
     }
 }
 
+// Level generation pass: the envs whose episode ended in the logic kernel just before (reset_list),
+// one warp each. Its launch is sized for the SM count, not for the list: a reset is one long serial
+// chain (RNG-driven generators), and a warp that has an SM sub-partition to itself runs it at the
+// latency of the chain instead of sharing issue slots with dozens of stepping warps.
+template <class G>
+__global__ void __launch_bounds__(32) reset_kernel(KParams p, unsigned int *ticket) {
+    using Frame = typename FrameFor<G>::type;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned count = *p.reset_count;
+    while (true) {
+        unsigned t = 0;
+        if (lane == 0)
+            t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= count)
+            break;
+        const int env = p.reset_list[t];
+        const long long t0 = p.dbg_cycles ? clock64() : 0;
+        env_reset_logic<G, Frame>(p, env);
+        __syncwarp();
+        if (p.dbg_cycles && lane == 0)
+            p.dbg_cycles[env] += (uint32_t)(clock64() - t0);
+    }
+}
+
 #ifndef PG_RENDER_CTAS_PER_SM
 #define PG_RENDER_CTAS_PER_SM 0  // 0 = as many as registers / the frame allow
 #endif
@@ -157,7 +182,14 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     using Frame = typename FrameFor<G>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Frame &f = *reinterpret_cast<Frame *>(smem_raw);
-    const int env = p.env_first + (int)blockIdx.x * p.env_step;
+    int env = p.env_first + (int)blockIdx.x * p.env_step;
+    if (p.render_mode == RENDER_LISTED) {  // the tail launch: envs that went through the reset pass
+        if (blockIdx.x >= *p.reset_count)
+            return;
+        env = p.reset_list[blockIdx.x];
+    } else if (p.render_mode == RENDER_SKIP_RESET && p.reset_epoch[env] == p.step_id) {
+        return;  // being regenerated right now; the tail launch draws it
+    }
     const int tid = (int)threadIdx.x;
 #ifdef PG_PHASE_TIMING
     long long t0 = clock64(), t1;
@@ -258,6 +290,9 @@ struct LaunchCtx {
     int max_logic_blocks;     // SM count x resident CTAs per SM
     int render_smem_floor;    // dynamic shared memory requested per render CTA is at least this (co-residency knob)
     cudaEvent_t *tev;         // optional: 3 events (before logic, between, after render) for kernel timing
+    cudaStream_t reset_stream;  // null: level generation stays inline in the logic kernel; else the stream of the reset pass
+    cudaEvent_t ev_logic, ev_reset;
+    int reset_blocks;         // grid of the reset kernel (1 warp per block)
 #endif
     int64_t *launch_counter;
 };
@@ -269,10 +304,14 @@ template <class G>
 int prepare_render_smem(const LaunchCtx &lc) {
     using Frame = typename FrameFor<G>::type;
     const int bytes = (int)sizeof(Frame) > lc.render_smem_floor ? (int)sizeof(Frame) : lc.render_smem_floor;
-    static int attr_set = 0;
-    if (attr_set < bytes) {
+    // the attribute is per device: remember what each device of this process was given
+    static int attr_set[64] = {};
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    int &have = attr_set[dev & 63];
+    if (have < bytes) {
         CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        attr_set = bytes;
+        have = bytes;
     }
     return bytes;
 }
@@ -293,31 +332,67 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     if (logic_blocks > lc.max_logic_blocks)
         logic_blocks = lc.max_logic_blocks;
     cudaStream_t ls = lc.logic_stream ? lc.logic_stream : lc.stream;
-    CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, sizeof(unsigned int), ls));
+    // lc.ticket = this launch slot's 4 counters: [0] logic tickets, [1] reset-list length, [2] reset tickets
+    CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, 4 * sizeof(unsigned int), ls));
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[0], ls));
-    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, ls>>>(p, lc.ticket);
+    KParams q = p;
+    const bool split = !INIT && p.reset_list != nullptr;
+    q.reset_count = split ? lc.ticket + 1 : nullptr;
+    q.render_mode = RENDER_ALL;
+    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, ls>>>(q, lc.ticket);
     if (lc.logic_stream) {
         CUDA_CHECK(cudaEventRecord(lc.link, ls));
         CUDA_CHECK(cudaStreamWaitEvent(lc.stream, lc.link, 0));
     }
-    if (lc.tev)
-        CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
-    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
-    if (lc.tev)
-        CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
+    int launches = 2;
+    if (split && lc.reset_stream) {
+        // level generation next to the rendering of everybody else: reset kernel + the tail render
+        // launch of the regenerated envs on the reset stream, the main render launch skips them
+        CUDA_CHECK(cudaEventRecord(lc.ev_logic, lc.stream));
+        CUDA_CHECK(cudaStreamWaitEvent(lc.reset_stream, lc.ev_logic, 0));
+        reset_kernel<G><<<lc.reset_blocks, 32, 0, lc.reset_stream>>>(q, lc.ticket + 2);
+        KParams qt = q;
+        qt.render_mode = RENDER_LISTED;
+        render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.reset_stream>>>(qt);
+        CUDA_CHECK(cudaEventRecord(lc.ev_reset, lc.reset_stream));
+        q.render_mode = RENDER_SKIP_RESET;
+        if (lc.tev)
+            CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
+        render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(q);
+        if (lc.tev)
+            CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
+        CUDA_CHECK(cudaStreamWaitEvent(lc.stream, lc.ev_reset, 0));
+        launches = 4;
+    } else {
+        if (split) {
+            reset_kernel<G><<<lc.reset_blocks, 32, 0, lc.stream>>>(q, lc.ticket + 2);
+            launches = 3;
+        }
+        if (lc.tev)
+            CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
+        render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(q);
+        if (lc.tev)
+            CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
+    }
     CUDA_CHECK(cudaGetLastError());
-    (*lc.launch_counter) += 2;
+    (*lc.launch_counter) += launches;
 #else
     static thread_local Frame *f = new Frame;
+    // the device's three passes in order: step logic, level generation of the envs it listed, frames
+    KParams q = p;
+    unsigned int n_reset = 0;
+    q.reset_count = (!INIT && p.reset_list != nullptr) ? &n_reset : nullptr;
+    q.render_mode = RENDER_ALL;
     for (int b = 0; b < p.env_count; b++) {
         int env = p.env_first + b * p.env_step;
         if (INIT)
-            env_init_logic<G, Frame>(p, env);
+            env_init_logic<G, Frame>(q, env);
         else
-            env_step_logic<G, Frame>(p, env);
-        render_env_serial<G, Frame>(p, env, *f);
+            env_step_logic<G, Frame>(q, env);
     }
+    for (unsigned t = 0; t < n_reset; t++) env_reset_logic<G, Frame>(q, q.reset_list[t]);
+    for (int b = 0; b < p.env_count; b++) render_env_serial<G, Frame>(q, p.env_first + b * p.env_step, *f);
     (*lc.launch_counter) += 2;
 #endif
 }
@@ -330,7 +405,9 @@ void launch_observe_only(const KParams &p, const LaunchCtx &lc) {
 #ifndef PG_HOSTSIM
     const int render_smem = prepare_render_smem<G>(lc);
     camera_kernel<G><<<p.env_count, 32, 0, lc.stream>>>(p);
-    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
+    KParams q = p;
+    q.render_mode = RENDER_ALL;
+    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(q);
     CUDA_CHECK(cudaGetLastError());
 #else
     static thread_local Frame *f = new Frame;
