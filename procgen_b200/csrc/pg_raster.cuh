@@ -134,6 +134,9 @@ struct FrameT {
     uint8_t col_p1[MAX_CELLS_1D], col_p2[MAX_CELLS_1D];  // device pixel span [p1,p2) of column i
     uint8_t row_p1[MAX_CELLS_1D], row_p2[MAX_CELLS_1D];
     uint8_t col_tw[MAX_CELLS_1D], row_th[MAX_CELLS_1D];  // snapped size if the column / row can use tiles, else 0
+    uint8_t col_k0[MAX_CELLS_1D], row_k0[MAX_CELLS_1D];  // pixels the device edge cuts off the near side (tile offset of the first visible one)
+    int32_t n_strip_cols;                                // pixel columns where two cell columns overlap
+    uint8_t strip_cols[RES_W];
     uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
     uint8_t row_lo[RES_H], row_hi[RES_H];
     uint32_t colinfo[RES_W], rowinfo[RES_H];  // CI_* words
@@ -1128,14 +1131,17 @@ struct Raster {
 
     // device pixel span [p1, p2) of a cell column / row, and (tile_size) its snapped size when the
     // column's cells are un-clipped on the near side so that pre-scaled tiles apply (else 0)
-    static PG_HD void span_of(double t, double tw, bool snap, int limit, uint8_t &p1, uint8_t &p2, uint8_t &tile_size) {
+    static PG_HD void span_of(double t, double tw, bool snap, int limit, uint8_t &p1, uint8_t &p2, uint8_t &tile_size, uint8_t &clip) {
         tile_size = 0;
+        clip = 0;
         if (snap) {
             double x = pg_qround(t);
             tw = pg_qround(t + tw - x);
             t = x;
-            if (x >= 0 && tw >= 1 && tw <= MAX_TILE_DIM)
+            if (tw >= 1 && tw <= MAX_TILE_DIM && x > -tw) {
                 tile_size = (uint8_t)(int)tw;
+                clip = x < 0 ? (uint8_t)(int)(-x) : 0;
+            }
         }
         int a = pg_qround(t), b2 = pg_qround(t + tw);
         if (a < 0) a = 0;
@@ -1181,6 +1187,7 @@ struct Raster {
             f.n_gen = 0;
             f.tile_top = 0;
             f.n_tjobs = 0;
+            f.n_strip_cols = 0;
             f.tile_w0 = f.tile_h0 = w0;
             f.rot = Frame::kRotInGlobal ? reinterpret_cast<RotBlit *>(c.rot_scratch_raw) : f.rot_local;
             if (Frame::kRotInGlobal && c.rot_scratch_raw == nullptr) {
@@ -1229,7 +1236,7 @@ struct Raster {
             if (i == 0)
                 f.cell_w = r[2];
             uint8_t ts;
-            span_of(r[0], r[2], snap, RES_W, f.col_p1[i], f.col_p2[i], ts);
+            span_of(r[0], r[2], snap, RES_W, f.col_p1[i], f.col_p2[i], ts, f.col_k0[i]);
             f.col_tw[i] = (ts == w0 || ts == w0 + 1) ? ts : 0;
         }
         for (int jj = tid; jj < ny; jj += nthreads) {
@@ -1238,13 +1245,14 @@ struct Raster {
             screen_rect(cam, (float)low_x, (float)(low_y + j + 1), 1, 1, RENDER_EPS, r);
             f.row_y[j] = r[1];
             uint8_t ts;
-            span_of(r[1], r[3], snap, RES_H, f.row_p1[j], f.row_p2[j], ts);
+            span_of(r[1], r[3], snap, RES_H, f.row_p1[j], f.row_p2[j], ts, f.row_k0[j]);
             f.row_th[j] = (ts == w0 || ts == w0 + 1) ? ts : 0;
         }
     }
 
     // cell columns (rows) covering pixel column (row) p -> lo / hi and the packed CI_* word
-    static PG_HD uint32_t cell_lookup(const uint8_t *p1, const uint8_t *p2, const uint8_t *tsize, int n, int base_mul, int px, uint8_t &lo, uint8_t &hi) {
+    static PG_HD uint32_t cell_lookup(const uint8_t *p1, const uint8_t *p2, const uint8_t *tsize, const uint8_t *k0, int n, int base_mul, int px, uint8_t &lo,
+                                      uint8_t &hi) {
         int l = 255, hgh = 0;
         for (int i = 0; i < n; i++) {
             if (px >= p1[i] && px < p2[i]) {
@@ -1261,7 +1269,7 @@ struct Raster {
         hi = (uint8_t)hgh;
         if (l == 255)
             return 0;
-        uint32_t w = (uint32_t)(hgh * base_mul) | CI_VALID | ((uint32_t)((px - p1[hgh]) & 31) << CI_D_SHIFT) | ((uint32_t)tsize[hgh] << CI_TW_SHIFT);
+        uint32_t w = (uint32_t)(hgh * base_mul) | CI_VALID | ((uint32_t)((px - p1[hgh] + k0[hgh]) & 31) << CI_D_SHIFT) | ((uint32_t)tsize[hgh] << CI_TW_SHIFT);
         if (l != hgh)
             w |= CI_MULTI;
         return w;
@@ -1516,6 +1524,22 @@ struct Raster {
         }
     }
 
+    // qt_scale_image_32bit's source walk along one axis for a target of snapped size `t` whose first `k0`
+    // pixels are cut off by the device edge (make_image_blit with tx = -k0, tx1 = 0) against the walk
+    // of the un-clipped target (the pre-scaled tile): same texel for every visible pixel?
+    static PG_HD bool clipped_walk_matches(int s, int t, int k0) {
+        if (k0 == 0)
+            return true;
+        const double sx = (double)s / (double)t;
+        const int ix = (int)(65536.0 * sx);
+        const uint32_t bu = (uint32_t)((int)pg_dceil((0 + 0.5 - 0.0) * sx * 65536) - 1);
+        const uint32_t bc = (uint32_t)((int)pg_dceil((0 + 0.5 - (double)(-k0)) * sx * 65536) - 1);
+        for (int j = 0; j + k0 < t; j++)
+            if (((bc + (uint32_t)ix * (uint32_t)j) >> 16) != ((bu + (uint32_t)ix * (uint32_t)(j + k0)) >> 16))
+                return false;
+        return true;
+    }
+
     // ---- phase C. Few entities: warp 0 builds the entity list while the other warps classify the
     // cells and build the pixel -> cell lookups. Many entities (bullet-heavy frames, tiled walls):
     // the whole CTA builds the list, then the cells.
@@ -1541,10 +1565,21 @@ struct Raster {
         if (!G::DRAWS_GRID)
             return;
         for (int px = wtid; px < RES_W + RES_H; px += wn) {
-            if (px < RES_W)
-                f.colinfo[px] = cell_lookup(f.col_p1, f.col_p2, f.col_tw, f.nx, f.ny, px, f.col_lo[px], f.col_hi[px]);
-            else
-                f.rowinfo[px - RES_W] = cell_lookup(f.row_p1, f.row_p2, f.row_th, f.ny, 1, px - RES_W, f.row_lo[px - RES_W], f.row_hi[px - RES_W]);
+            if (px < RES_W) {
+                const uint32_t w = cell_lookup(f.col_p1, f.col_p2, f.col_tw, f.col_k0, f.nx, f.ny, px, f.col_lo[px], f.col_hi[px]);
+                f.colinfo[px] = w;
+                if (w & CI_MULTI) {
+                    int slot;
+#if defined(__CUDA_ARCH__)
+                    slot = atomicAdd(&f.n_strip_cols, 1);
+#else
+                    slot = f.n_strip_cols++;
+#endif
+                    f.strip_cols[slot] = (uint8_t)px;
+                }
+            } else {
+                f.rowinfo[px - RES_W] = cell_lookup(f.row_p1, f.row_p2, f.row_th, f.row_k0, f.ny, 1, px - RES_W, f.row_lo[px - RES_W], f.row_hi[px - RES_W]);
+            }
         }
         // Cells, pass A (draw_grid_obj / draw_image for a grid cell, basic-abstract-game.cpp:877-919,
         // 940-950): a cell whose sprite can come from the pre-scaled tile table only registers the
@@ -1565,7 +1600,15 @@ struct Raster {
             if (tw && th && !mono && type >= 0 && type < CELL_KEY_TYPES && theme >= 0 && theme < MAX_IMAGE_THEMES) {
                 const int img_type = G::image_for_type(c, type);
                 double adj[4];
-                if (img_type >= 0 && img_type < USE_ASSET_THRESHOLD && !G::get_adjusted_image_rect(c, img_type, adj)) {
+                bool ok = img_type >= 0 && img_type < USE_ASSET_THRESHOLD && !G::get_adjusted_image_rect(c, img_type, adj);
+                if (ok && (f.col_k0[ci] | f.row_k0[cj])) {
+                    // a cell the near device edge cuts: its blit starts its 16.16 walk from the first visible
+                    // pixel, the tile from the un-clipped origin — usable only if both visit the same texels
+                    const int masked_theme = (c.h->options.restrict_themes && !G::should_preserve_type_themes(c, img_type)) ? 0 : theme;
+                    const SpriteDesc sd = c.assets->sprites[img_type + masked_theme * MAX_ASSETS];
+                    ok = sd.w != 0 && clipped_walk_matches(sd.w, tw, f.col_k0[ci]) && clipped_walk_matches(sd.h, th, f.row_k0[cj]);
+                }
+                if (ok) {
                     const int key = type * 4 + (tw - f.tile_w0) + 2 * (th - f.tile_h0);
                     f.tilekey[key] = 1;  // benign race: every writer stores 1
                     f.cellmap[k] = (uint16_t)(0x4000 | key);
@@ -1727,7 +1770,7 @@ struct Raster {
     static PG_HD uint32_t cell_layer(const Frame &f, uint32_t code, int ci, int cj, int px, int py, const uint32_t *atlas) {
         if (code & CELL_GENERAL)
             return blit_texel(*f.gen_blit((int)(code & 0x7fffu)), px, py, atlas, f.rot);
-        const int dx = px - f.col_p1[ci], dy = py - f.row_p1[cj];
+        const int dx = px - f.col_p1[ci] + f.col_k0[ci], dy = py - f.row_p1[cj] + f.row_k0[cj];
         return f.arena[(int)code - 1 + dy * f.col_tw[ci] + dx];
     }
 
@@ -1749,9 +1792,9 @@ struct Raster {
         return dst;
     }
 
-    // all cells over `under` at one pixel, in draw order (x outer / y inner): the out-of-line path
-    // for pixels where neighbouring cells overlap or a cell is a general blit
-    static PG_HD_NOINLINE uint32_t cells_generic(const Frame &f, int px, int py, const uint32_t *atlas, uint32_t under) {
+    // all cells over `under` at one pixel, in draw order (x outer / y inner): pixels where neighbouring
+    // cells overlap (the strips) or a cell is a general blit
+    static PG_HD uint32_t cells_over(const Frame &f, int px, int py, const uint32_t *atlas, uint32_t under) {
         uint32_t dst = under;
         const int clo = f.col_lo[px], chi = f.col_hi[px], rlo = f.row_lo[py], rhi = f.row_hi[py];
         if (clo != 255 && rlo != 255) {
@@ -1763,6 +1806,9 @@ struct Raster {
                 }
         }
         return dst;
+    }
+    static PG_HD_NOINLINE uint32_t cells_generic(const Frame &f, int px, int py, const uint32_t *atlas, uint32_t under) {
+        return cells_over(f, px, py, atlas, under);
     }
 
     // What a thread keeps for the four pixel columns of its quad while it walks down the rows.
@@ -1795,7 +1841,7 @@ struct Raster {
             bool slow = false;
             if (G::DRAWS_GRID && MODE != GATHER_BG && (ci & rowinfo & CI_VALID)) {
                 if ((ci | rowinfo) & CI_MULTI) {
-                    slow = true;
+                    continue;  // a strip where cells overlap: left to gather_strips
                 } else {
                     const uint32_t code = f.cellmap[(ci & CI_BASE_MASK) + (rowinfo & CI_BASE_MASK)];
                     if (code & CELL_GENERAL)
@@ -1819,6 +1865,39 @@ struct Raster {
                 dst[k] = cells_generic(f, px0 + k, py, atlas, under);
             else
                 dst[k] = s != 0 ? s + pg_byte_mul(under, (~s) >> 24) : under;
+        }
+    }
+
+    // The pixels gather_quad skipped: where neighbouring cell columns (rows) overlap by a pixel, up
+    // to 2 x 2 cells lie over each other. Those strips are a few pixel columns and rows of the frame;
+    // walked here densely (a lane = one strip pixel) they cost a fraction of what they cost as
+    // divergent branches of the quad loop.
+    template <int MODE>
+    static PG_HD void gather_strips(const Frame &f, uint32_t *fb, int row_first, int row_step, int lane, int nlanes, const uint32_t *atlas) {
+        const int my_rows = (RES_H - row_first + row_step - 1) / row_step;
+        // strip columns x my rows
+        const int n1 = f.n_strip_cols * my_rows;
+        for (int idx = lane; idx < n1; idx += nlanes) {
+            const int px = f.strip_cols[idx / my_rows], py = row_first + (idx % my_rows) * row_step;
+            if (!(f.rowinfo[py] & CI_VALID))
+                continue;  // no cell row here: gather_quad drew the pixel
+            uint32_t *dst = fb + py * RES_W + px;
+            const uint32_t under = MODE == GATHER_CELLS ? *dst : bg_generic(f, px, py, atlas);
+            *dst = cells_over(f, px, py, atlas, under);
+        }
+        // strip rows among my rows x the other columns
+        for (int r = 0; r < my_rows; r++) {
+            const int py = row_first + r * row_step;
+            if (!(f.rowinfo[py] & CI_MULTI))
+                continue;
+            for (int px = lane; px < RES_W; px += nlanes) {
+                const uint32_t ci = f.colinfo[px];
+                if (!(ci & CI_VALID) || (ci & CI_MULTI))
+                    continue;
+                uint32_t *dst = fb + py * RES_W + px;
+                const uint32_t under = MODE == GATHER_CELLS ? *dst : bg_generic(f, px, py, atlas);
+                *dst = cells_over(f, px, py, atlas, under);
+            }
         }
     }
 
@@ -1894,6 +1973,8 @@ struct Raster {
                 for (int py = first; py < RES_H; py += row_step * sub) gather_quad<GATHER_ALL>(f, q, qx * 4, py, atlas, fb);
             }
         }
+        if (G::DRAWS_GRID && !(G::ENTS_BELOW_GRID && nb > 0))
+            gather_strips<GATHER_ALL>(f, fb, row_first, row_step, lane, nlanes, atlas);
         if (G::ENTS_BELOW_GRID && nb > 0) {
 #if defined(__CUDA_ARCH__)
             __syncwarp();
@@ -1905,6 +1986,8 @@ struct Raster {
                 const int first = row_first + row_step * (nlanes >= per_row ? lane / per_row : 0);
                 for (int py = first; py < RES_H; py += row_step * sub) gather_quad<GATHER_CELLS>(f, q, qx * 4, py, atlas, fb);
             }
+            if (G::DRAWS_GRID)
+                gather_strips<GATHER_CELLS>(f, fb, row_first, row_step, lane, nlanes, atlas);
         }
 #if defined(__CUDA_ARCH__)
         __syncwarp();
