@@ -345,6 +345,10 @@ def run_ours(args):
     # ---- e2e: the reference-facing C ABI with host buffers, H2D/D2H inside the timed region
     e2e = None
     if not args.no_e2e:
+        from procgen_b200.numa import pin_to_gpu_numa_node
+
+        saved_affinity = os.sched_getaffinity(0)
+        numa = pin_to_gpu_numa_node(torch.cuda.current_device()) if not args.no_numa_pin else {"pinned": False}
         Ke = max(3, min(args.e2e_steps, K))
         henv = ProcgenGym3Env(n, args.game, distribution_mode=args.mode, num_levels=0, start_level=0, rand_seed=0,
                               shard=(rank, world) if world > 1 else None, host_buffers=True)
@@ -362,9 +366,10 @@ def run_ours(args):
         d2h = (64 * 64 * 3 + 4 + 1 + 4 + 1 + 4) * n
         e2e = {"value": n * world * Ke / el, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n * world,
                "d2h_bytes_per_step": d2h * world, "steps": Ke, "d2h_gbs_per_rank": d2h * Ke / el / 1e9,
-               "api": "libenv_act + libenv_observe (host numpy buffers)", "timer": "host perf_counter around the calls",
+               "numa": numa, "api": "libenv_act + libenv_observe (host numpy buffers, page-locked)", "timer": "host perf_counter around the calls",
                "note": "cold start (synchronised episodes); PCIe-bound, so level generation does not show"}
         henv.close()
+        os.sched_setaffinity(0, saved_affinity)   # the CPU baseline below gets every core back
 
     # ---- BASELINE configs[4] riding along on multi-GPU runs: the 16-game list, 32 768 envs per GPU,
     # without and with the per-step NCCL gather of every rank's rgb shard to rank 0
@@ -475,6 +480,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-pin", action="store_true", help="e2e leg: do not pin the process to the GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--desync-steps", type=int, default=1500,
                     help="untimed rollout before the steady-state measurement (episodes ~500-1000 steps)")

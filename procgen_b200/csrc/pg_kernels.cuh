@@ -140,7 +140,9 @@ __device__ __forceinline__ void env_prefetch(const KParams &p, int env) {
 #endif
 
 // Game::step (game.cpp:120-155) up to, not including, the pixel work. One thread.
-template <class G, class Frame>
+// SPLIT: level generation is left to the reset pass (the code of reset() is then not even part of
+// the kernel that steps the envs, which keeps it within reach of the instruction cache)
+template <class G, class Frame, bool SPLIT>
 PG_HD void env_step_logic(const KParams &p, int env) {
 #if defined(__CUDA_ARCH__)
     env_prefetch(p, env);
@@ -148,7 +150,7 @@ PG_HD void env_step_logic(const KParams &p, int env) {
     Ctx c = make_ctx(p, env);
     c.h->action = p.action[env];  // vecgame.cpp:388
     const bool ended = Engine<G>::step_play(c);
-    if (ended && p.reset_count != nullptr) {
+    if (SPLIT && ended) {
         // level generation runs in the reset pass; it also finishes the step there
 #if defined(__CUDA_ARCH__)
         if ((threadIdx.x & 31u) == 0) {
@@ -162,7 +164,7 @@ PG_HD void env_step_logic(const KParams &p, int env) {
 #endif
         return;
     }
-    Engine<G>::step_finish(c, ended);
+    Engine<G>::step_finish(c, SPLIT ? false : ended);
     Raster<G, Frame>::prepare_camera(c);
     write_step_outputs(p, env, *c.h);
 }

@@ -69,7 +69,7 @@ constexpr int kRenderThreads = 128;
 // Persistent: the grid is sized to fill the machine once and every warp pulls env indices from a
 // global ticket counter until the launch's range is exhausted, so a long env (level reset) only
 // delays its own warp and no SM slot idles waiting for a block launch.
-template <class G, bool INIT>
+template <class G, bool INIT, bool SPLIT>
 __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kernel(KParams p, unsigned int *ticket) {
     using Frame = typename FrameFor<G>::type;
     const unsigned lane = threadIdx.x & 31u;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kern
         if (INIT)
             env_init_logic<G, Frame>(p, env);
         else
-            env_step_logic<G, Frame>(p, env);
+            env_step_logic<G, Frame, SPLIT>(p, env);
         __syncwarp();
         if (p.dbg_cycles && lane == 0)
             p.dbg_cycles[env] = (uint32_t)(clock64() - t0);
@@ -340,7 +340,10 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     const bool split = !INIT && p.reset_list != nullptr;
     q.reset_count = split ? lc.ticket + 1 : nullptr;
     q.render_mode = RENDER_ALL;
-    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, ls>>>(q, lc.ticket);
+    if (split)
+        logic_kernel<G, false, true><<<logic_blocks, kLogicThreads, 0, ls>>>(q, lc.ticket);
+    else
+        logic_kernel<G, INIT, false><<<logic_blocks, kLogicThreads, 0, ls>>>(q, lc.ticket);
     if (lc.logic_stream) {
         CUDA_CHECK(cudaEventRecord(lc.link, ls));
         CUDA_CHECK(cudaStreamWaitEvent(lc.stream, lc.link, 0));
@@ -388,8 +391,10 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
         int env = p.env_first + b * p.env_step;
         if (INIT)
             env_init_logic<G, Frame>(q, env);
+        else if (q.reset_count)
+            env_step_logic<G, Frame, true>(q, env);
         else
-            env_step_logic<G, Frame>(q, env);
+            env_step_logic<G, Frame, false>(q, env);
     }
     for (unsigned t = 0; t < n_reset; t++) env_reset_logic<G, Frame>(q, q.reset_list[t]);
     for (int b = 0; b < p.env_count; b++) render_env_serial<G, Frame>(q, p.env_first + b * p.env_step, *f);

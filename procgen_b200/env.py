@@ -174,7 +174,17 @@ class BaseProcgenEnv:
     # ------------------------------------------------------------------ buffer plumbing
     def _setup_host_buffers(self):
         n = self.num
-        self._rgb = np.zeros((n, 64, 64, 3), np.uint8)
+        self._rgb = None
+        if self._torch is not None:
+            try:
+                # page-locked from the start (cudaHostAlloc through torch): the library then DMAs straight
+                # into it without having to register 12 KiB/env of pageable memory
+                self._rgb_pinned = self._torch.zeros((n, 64, 64, 3), dtype=self._torch.uint8, pin_memory=True)
+                self._rgb = self._rgb_pinned.numpy()
+            except Exception:
+                self._rgb = None
+        if self._rgb is None:
+            self._rgb = np.zeros((n, 64, 64, 3), np.uint8)
         self._rew = np.zeros(n, np.float32)
         self._first = np.zeros(n, np.uint8)
         self._ac = np.zeros(n, np.int32)
