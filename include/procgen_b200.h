@@ -194,6 +194,18 @@ LIBENV_API int pgb200_debug_read_env(libenv_env *handle, int env, void *hdr_out,
 LIBENV_API int pgb200_set_rgb_mirror(libenv_env *handle, void *mirror0, void *mirror1);
 LIBENV_API int pgb200_mirror_parity(libenv_env *handle);
 
+/* Consumer epilogue (the uint8 -> float normalise + frame-stack step that train-procgen style
+ * learners run on every observation, README.md:13): a second output written by the render kernel.
+ * `buffer` = device memory of [num_envs][slots][3][64][64] 16-bit floats, dtype 1 = fp16, 2 = bf16,
+ * value = rgb / 255 (fp32 division, rounded to nearest even), planar CHW, slots = 1 for k_frames == 1
+ * else 2*k_frames: the frame of step t goes to ring slots s = t mod k and s + k, so the ordered stack
+ * (oldest first) is always the contiguous slot range [s + 1, s + k] (pgb200_consumer_slot = s). When
+ * an env starts an episode the older frames of its window are zeroed (baselines' VecFrameStack). At
+ * the call the current frames are written as step 0. buffer == NULL or dtype == 0 switches it off.
+ * Returns 0, -1 on bad arguments or in the host debug build. */
+LIBENV_API int pgb200_set_consumer_output(libenv_env *handle, void *buffer, int dtype, int k_frames);
+LIBENV_API int pgb200_consumer_slot(libenv_env *handle);
+
 /* Introspection: shared memory of one render CTA (the per-game frame) and the number of render CTAs
  * per SM the render kernel of `game` is compiled for. Returns -1 for an unknown game. */
 LIBENV_API int pgb200_frame_info(const char *game, int *frame_bytes, int *ctas_per_sm);

@@ -41,6 +41,12 @@ struct KParams {
     int32_t fixed_asset_seed;   // FNV-1a of the game name (vecgame.cpp:156-167, 324-327)
     int32_t snap;
     int32_t env_global_offset;  // game_n = env_global_offset + env
+    // optional second output for on-device learners: normalised fp16 / bf16, planar
+    // CHW, k-frame stack kept as a 2k-slot ring so that the ordered stack is always one contiguous view
+    void *consumer;             // [N][slots][3][64][64] 16-bit elements; null = off
+    const uint16_t *consumer_lut;  // [256] = (16-bit float)(v / 255.f)
+    int32_t consumer_k;         // frames per stack; slots = k == 1 ? 1 : 2k
+    int32_t consumer_slot;      // ring position this step writes: t mod k
     // level generation as its own pass (see pg_launch.cuh): envs whose episode ended this step
     int32_t *reset_list;        // this launch's segment: env indices, filled by the logic kernel
     unsigned int *reset_count;  // entries in reset_list (null: resets run inline in the logic kernel)

@@ -232,6 +232,37 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     env_render_compose<G, Frame>(p, f, tid >> 5, kRenderThreads >> 5, tid & 31, 32);
     __syncthreads();
     PG_RENDER_PHASE(11);
+    if (p.consumer != nullptr) {
+        // Consumer epilogue: the frame as normalised 16-bit floats, planar, into ring slot s (and its
+        // twin s + k); an env that starts an episode this step gets the older frames of its window
+        // zeroed (the frame-stack convention of baselines' VecFrameStack). Thread = pixel pairs.
+        const int kf = p.consumer_k, s = p.consumer_slot;
+        const int slots = kf == 1 ? 1 : 2 * kf;
+        uint32_t *base = reinterpret_cast<uint32_t *>(p.consumer) + (size_t)env * slots * (3 * RES_W * RES_H / 2);
+        const uint16_t *lut = p.consumer_lut;
+        for (int pair = tid; pair < RES_W * RES_H / 2; pair += kRenderThreads) {
+            const uint32_t c0 = f.fb[2 * pair], c1 = f.fb[2 * pair + 1];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const int sh = 16 - 8 * ch;  // R, G, B planes
+                const uint32_t v = (uint32_t)lut[(c0 >> sh) & 0xffu] | ((uint32_t)lut[(c1 >> sh) & 0xffu] << 16);
+                base[(size_t)(s * 3 + ch) * (RES_W * RES_H / 2) + pair] = v;
+                if (kf > 1)
+                    base[(size_t)((s + kf) * 3 + ch) * (RES_W * RES_H / 2) + pair] = v;
+            }
+        }
+        if (kf > 1 && p.first[env]) {
+            // window of this step = ring slots s+1 .. s+k (the newest is s+k); zero the k-1 older ones
+            // wherever they live: slot j and its twin j +- k
+            for (int j = 1; j < kf; j++) {
+                const int a = (s + j) % kf;
+                for (int w = tid; w < 3 * RES_W * RES_H / 2; w += kRenderThreads) {
+                    base[(size_t)a * (3 * RES_W * RES_H / 2) + w] = 0u;
+                    base[(size_t)(a + kf) * (3 * RES_W * RES_H / 2) + w] = 0u;
+                }
+            }
+        }
+    }
     {
         // RGB32 -> RGB888 in place: every thread reads its 8 pixel quads, then (barrier) writes them packed
         constexpr int kQuadsPerThread = RES_W * RES_H / 4 / kRenderThreads;

@@ -40,6 +40,7 @@
 #include "pg_state_io.h"
 
 #ifndef PG_HOSTSIM
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #endif
 
@@ -192,6 +193,20 @@ __global__ void tile_table_kernel(const SpriteDesc *sprites, const uint32_t *ind
 }
 #endif
 
+#ifndef PG_HOSTSIM
+// (16-bit float)(v / 255.f) for v = 0..255: IEEE fp32 division, then round-to-nearest-even
+__global__ void consumer_lut_kernel(uint16_t *lut, int bf16) {
+    const int v = (int)threadIdx.x;
+    const float x = __fdiv_rn((float)v, 255.0f);
+    if (bf16) {
+        const uint32_t u = __float_as_uint(x);
+        lut[v] = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+    } else {
+        lut[v] = __half_as_ushort(__float2half_rn(x));
+    }
+}
+#endif
+
 // ================================================================= VecEnv (VecGame, vecgame.h)
 struct VecEnv {
     int num_envs = 0;
@@ -250,6 +265,8 @@ struct VecEnv {
     // these buffers (another GPU's memory, mapped through NVLink) right behind its render kernel
     uint8_t *mirror[2] = {nullptr, nullptr};
     int mirror_parity = 0;
+    uint16_t *d_consumer_lut = nullptr;
+    int64_t consumer_steps = 0;
     bool have_host_bufs = false;
     bool rgb_copy_enqueued = false;  // this step's observation DMA already follows the render kernels
     bool ob_direct = false;      // caller's obs block is contiguous and page-locked: DMA straight into it
@@ -312,6 +329,10 @@ struct VecEnv {
             mirror_parity ^= 1;
         if (!init)
             step_id++;
+        if (!init && base.consumer) {
+            consumer_steps++;
+            base.consumer_slot = (int32_t)(consumer_steps % base.consumer_k);
+        }
         int k = 0;
         for (int g = 0; g < G; g++) {
             for (int cidx = 0; cidx < chunks; cidx++, k++) {
@@ -932,6 +953,7 @@ void libenv_close(libenv_env *handle) {
     dev_free(v->d_lvl_seeds);
     dev_free(v->d_reset_list);
     dev_free(v->d_reset_epoch);
+    dev_free(v->d_consumer_lut);
     if (p.dbg_cycles)
         dev_free(p.dbg_cycles);
 #ifndef PG_HOSTSIM
@@ -1028,6 +1050,48 @@ int pgb200_set_rgb_mirror(libenv_env *handle, void *mirror0, void *mirror1) {
     return -1;
 #endif
 }
+
+int pgb200_set_consumer_output(libenv_env *handle, void *buffer, int dtype, int k_frames) {
+#ifndef PG_HOSTSIM
+    VecEnv *v = (VecEnv *)handle;
+    v->set_device();
+    v->ensure_initial_reset();
+    v->sync();
+    if (buffer == nullptr || dtype == 0) {
+        v->base.consumer = nullptr;
+        return 0;
+    }
+    if ((dtype != 1 && dtype != 2) || k_frames < 1 || k_frames > 16)
+        return -1;
+    if (!v->d_consumer_lut)
+        v->d_consumer_lut = dev_alloc<uint16_t>(256);
+    consumer_lut_kernel<<<1, 256, 0, v->stream>>>(v->d_consumer_lut, dtype == 2);
+    CUDA_CHECK(cudaGetLastError());
+    v->base.consumer = buffer;
+    v->base.consumer_lut = v->d_consumer_lut;
+    v->base.consumer_k = k_frames;
+    v->base.consumer_slot = 0;
+    v->consumer_steps = 0;
+    // the current frame of every env becomes the newest frame of an otherwise empty stack
+    for (size_t g = 0; g < v->games.size(); g++) {
+        KParams p = v->base;
+        p.assets = v->d_assets[g];
+        p.game_id = v->games[g]->id;
+        p.env_first = (int)g;
+        p.env_step = (int)v->games.size();
+        p.env_count = v->num_envs / (int)v->games.size();
+        LaunchCtx lc = v->lctx();
+        v->games[g]->observe_only(p, lc);
+    }
+    v->sync();
+    return 0;
+#else
+    (void)handle; (void)buffer; (void)dtype; (void)k_frames;
+    return -1;
+#endif
+}
+
+int pgb200_consumer_slot(libenv_env *handle) { return ((VecEnv *)handle)->base.consumer_slot; }
 
 int pgb200_mirror_parity(libenv_env *handle) { return ((VecEnv *)handle)->mirror_parity; }
 

@@ -410,6 +410,32 @@ class BaseProcgenEnv:
         dist.gather(self._rgb, None, dst=dst)
         return None
 
+    # ------------------------------------------------------------------ consumer epilogue
+    def enable_consumer_output(self, dtype=None, frames: int = 1):
+        """Have the render kernel also write what a learner feeds its network: rgb / 255 as float16 or
+        bfloat16, planar CHW, `frames` frames stacked along the channel axis with baselines'
+        VecFrameStack reset rule (an env that starts an episode sees zeros for the older frames).
+        consumer_observation() then returns [num, 3*frames, 64, 64] without any further kernel."""
+        torch = self._torch
+        dtype = dtype or torch.float16
+        code = {torch.float16: 1, torch.bfloat16: 2}[dtype]
+        slots = 1 if frames == 1 else 2 * frames
+        with torch.cuda.device(self._dev):
+            self._consumer = torch.zeros((self.num, slots, 3, 64, 64), dtype=dtype, device=self._dev)
+            self._consumer_k = int(frames)
+            torch.cuda.current_stream(self._dev).synchronize()
+            rc = self._lib.pgb200_set_consumer_output(self._h, C.c_void_p(self._consumer.data_ptr()), code, int(frames))
+        if rc != 0:
+            raise ValueError("pgb200_set_consumer_output rejected the arguments")
+
+    def consumer_observation(self):
+        """[num, 3*frames, 64, 64] view (oldest frame first) of the consumer output; valid until the next act()."""
+        k = self._consumer_k
+        if k == 1:
+            return self._consumer[:, 0]
+        s = int(self._lib.pgb200_consumer_slot(self._h))
+        return self._consumer[:, s + 1:s + 1 + k].reshape(self.num, 3 * k, 64, 64)
+
     def gather_how(self) -> str:
         if getattr(self, "_peer", None) is not None:
             return ("peer writes: each render launch is followed by a copy of its frames into rank-0 symmetric memory over "
@@ -418,6 +444,9 @@ class BaseProcgenEnv:
             f" (peer path unavailable: {self._peer_error})" if getattr(self, "_peer_error", None) else "")
 
     def close(self):
+        if getattr(self, "_consumer", None) is not None and getattr(self, "_h", None):
+            self._lib.pgb200_set_consumer_output(self._h, None, 0, 0)
+            self._consumer = None
         if getattr(self, "_peer", None) is not None and getattr(self, "_h", None):
             self._lib.pgb200_set_rgb_mirror(self._h, None, None)
             self._peer = None

@@ -48,7 +48,8 @@ EXPORTS = ["libenv_version", "libenv_make", "libenv_get_tensortypes", "libenv_se
            "libenv_act", "libenv_close", "pgb200_get_device_buffers", "pgb200_set_stream", "pgb200_act_device",
            "pgb200_sync", "pgb200_get_errors", "pgb200_debug_cycles", "pgb200_debug_read_env", "pgb200_kernel_launches", "pgb200_is_device_build",
            "pgb200_kernel_timing_begin", "pgb200_kernel_timing_end", "get_state", "set_state", "pgb200_set_launch_shape",
-           "pgb200_frame_info", "pgb200_set_rgb_mirror", "pgb200_mirror_parity"]
+           "pgb200_frame_info", "pgb200_set_rgb_mirror", "pgb200_mirror_parity",
+           "pgb200_set_consumer_output", "pgb200_consumer_slot"]
 
 _lib = None
 
@@ -78,6 +79,10 @@ def bind(lib):
     lib.pgb200_frame_info.restype = C.c_int
     lib.pgb200_set_rgb_mirror.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pgb200_set_rgb_mirror.restype = C.c_int
+    lib.pgb200_set_consumer_output.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.pgb200_set_consumer_output.restype = C.c_int
+    lib.pgb200_consumer_slot.argtypes = [C.c_void_p]
+    lib.pgb200_consumer_slot.restype = C.c_int
     lib.pgb200_mirror_parity.argtypes = [C.c_void_p]
     lib.pgb200_mirror_parity.restype = C.c_int
     lib.pgb200_kernel_launches.argtypes = [C.c_void_p]

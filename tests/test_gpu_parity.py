@@ -341,3 +341,42 @@ def test_baselines_vecenv_and_gym_wrappers(ref_lib, product_lib):
         assert info["level_seed"] == int(ref.info["level_seed"][0])
     genv.close()
     ref.close()
+
+
+@pytest.mark.parametrize("name,frames,dtype_name", [("coinrun", 4, "float16"), ("bigfish", 1, "bfloat16"), ("maze", 3, "bfloat16")])
+def test_consumer_epilogue_matches_torch_ops(product_lib, name, frames, dtype_name):
+    """the render kernel's second output (rgb / 255 as 16-bit floats, planar CHW, k-frame
+    stack with the VecFrameStack reset rule) equals the same thing computed with torch ops on the
+    uint8 observation, element for element."""
+    import torch
+
+    from procgen_b200 import ProcgenGym3Env
+
+    dtype = getattr(torch, dtype_name)
+    n = 256
+    env = ProcgenGym3Env(n, name, distribution_mode="easy", num_levels=0, start_level=0, rand_seed=2)
+    env.enable_consumer_output(dtype=dtype, frames=frames)
+
+    def to_planes(rgb):
+        return (rgb.permute(0, 3, 1, 2).to(torch.float32) / 255.0).to(dtype)
+
+    rew, ob, first = env.observe()
+    stack = [torch.zeros((n, 3, 64, 64), dtype=dtype, device="cuda") for _ in range(frames - 1)] + [to_planes(ob["rgb"])]
+    assert torch.equal(env.consumer_observation(), torch.cat(stack, dim=1))
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    resets = 0
+    for t in range(300):
+        env.act(torch.randint(0, 15, (n,), device="cuda", dtype=torch.int32, generator=gen))
+        rew, ob, first = env.observe()
+        newest = to_planes(ob["rgb"])
+        stack = stack[1:] + [newest]
+        if frames > 1 and bool(first.any()):
+            for old in stack[:-1]:
+                old[first] = 0
+        resets += int(first.sum())
+        got = env.consumer_observation()
+        assert got.shape == (n, 3 * frames, 64, 64)
+        assert torch.equal(got, torch.cat(stack, dim=1)), f"step {t}"
+        stack = [x.clone() for x in stack]
+    assert resets > 0 and env.errors() == 0
+    env.close()
