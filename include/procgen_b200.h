@@ -206,6 +206,10 @@ LIBENV_API int pgb200_mirror_parity(libenv_env *handle);
 LIBENV_API int pgb200_set_consumer_output(libenv_env *handle, void *buffer, int dtype, int k_frames);
 LIBENV_API int pgb200_consumer_slot(libenv_env *handle);
 
+/* Profiling variant only (-DPG_PHASE_TIMING): byte offset of the 12 phase-cycle counters inside the
+ * header pgb200_debug_read_env returns; -1 in the product build. */
+LIBENV_API int pgb200_debug_phase_offset(void);
+
 /* Introspection: shared memory of one render CTA (the per-game frame) and the number of render CTAs
  * per SM the render kernel of `game` is compiled for. Returns -1 for an unknown game. */
 LIBENV_API int pgb200_frame_info(const char *game, int *frame_bytes, int *ctas_per_sm);

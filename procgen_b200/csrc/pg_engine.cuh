@@ -299,15 +299,24 @@ struct Engine {
     static PG_HD void choose_step_random_theme(Ctx &c, Entity &ent) {
         ent.image_theme = c.h->step_rand_int % c.assets->num_themes[ent.image_type];
     }
+    // initialize_asset_if_necessary (basic-abstract-game.cpp:79-123) fills slot [type + 100 * theme] with
+    // the image of the MASKED theme (:86), so under restrict_themes the aspect ratio game logic reads
+    // for any theme is theme 0's
+    static PG_HD int asset_slot(Ctx &c, const Entity &ent) {
+        int theme = ent.image_theme;
+        if (c.h->options.restrict_themes && !G::should_preserve_type_themes(c, ent.image_type))
+            theme = 0;
+        return ent.image_type + theme * MAX_ASSETS;
+    }
     static PG_HD void match_aspect_ratio(Ctx &c, Entity &ent, bool match_width = true) {
-        int img_idx = ent.image_type + ent.image_theme * MAX_ASSETS;
+        int img_idx = asset_slot(c, ent);
         if (match_width)
             ent.ry = ent.rx / c.assets->aspect[img_idx];
         else
             ent.rx = ent.ry * c.assets->aspect[img_idx];
     }
     static PG_HD void fit_aspect_ratio(Ctx &c, Entity &ent) {
-        int img_idx = ent.image_type + ent.image_theme * MAX_ASSETS;
+        int img_idx = asset_slot(c, ent);
         float ar = c.assets->aspect[img_idx];
         if (ar > 1)
             ent.ry = ent.rx / ar;

@@ -204,8 +204,15 @@ PG_HD void env_render_jobs(const KParams &p, int env, Frame &f, int tid, int nth
     Raster<G, Frame>::frame_tile_alloc(c, f, p.tiles, tid, nthreads);
     if (f.n_jobs > 0)
         Raster<G, Frame>::frame_tiles(c, f, tid, nthreads);
-    if (G::DEFER_ROTATED)
+    if (G::DEFER_ROTATED) {
+#if defined(__CUDA_ARCH__)
+        // frame_rots scans the whole list for reserved slots; the slots frame_tiles fills hold stale
+        // bytes until it has written them (block-uniform condition)
+        if (f.n_jobs > 0)
+            __syncthreads();
+#endif
         Raster<G, Frame>::frame_rots(c, f, tid, nthreads);
+    }
     if (tid == nthreads - 1)
         Raster<G, Frame>::frame_append_overlays(f);
 }

@@ -207,12 +207,13 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
         pg_mbar_init(&f.mbar, 1);
     env_render_begin<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
-    PG_RENDER_PHASE(8);
+    PG_RENDER_PHASE(0);
     env_render_build<G, Frame>(p, env, f, tid, kRenderThreads, 32);
     __syncthreads();
+    PG_RENDER_PHASE(1);
     env_render_jobs<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
-    PG_RENDER_PHASE(9);
+    PG_RENDER_PHASE(2);
     if (G::DRAWS_GRID && tid < 32) {
         const int nj = f.n_tjobs < MAX_TILE_JOBS ? f.n_tjobs : MAX_TILE_JOBS;
         if (tid == 0) {
@@ -225,13 +226,14 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     }
     env_render_masks<G, Frame>(p, env, f, tid, kRenderThreads);
     __syncthreads();
-    PG_RENDER_PHASE(10);
+    PG_RENDER_PHASE(3);
     if (G::DRAWS_GRID)
         pg_mbar_wait(&f.mbar, 0);
+    PG_RENDER_PHASE(4);
     // warp w owns rows y = w (mod warps): gather and paint need no block barrier in between
     env_render_compose<G, Frame>(p, f, tid >> 5, kRenderThreads >> 5, tid & 31, 32);
     __syncthreads();
-    PG_RENDER_PHASE(11);
+    PG_RENDER_PHASE(5);
     if (p.consumer != nullptr) {
         // Consumer epilogue: the frame as normalised 16-bit floats, planar, into ring slot s (and its
         // twin s + k); an env that starts an episode this step gets the older frames of its window
@@ -278,8 +280,10 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of f.fb -> visible to the bulk copy
     __syncthreads();
+    PG_RENDER_PHASE(6);
     if (tid == 0)
         pg_bulk_store_and_wait(p.rgb + (size_t)env * (RES_W * RES_H * 3), f.fb, RES_W * RES_H * 3);
+    PG_RENDER_PHASE(7);
 #undef PG_RENDER_PHASE
 }
 

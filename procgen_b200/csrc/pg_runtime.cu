@@ -1091,6 +1091,14 @@ int pgb200_set_consumer_output(libenv_env *handle, void *buffer, int dtype, int 
 #endif
 }
 
+int pgb200_debug_phase_offset(void) {
+#ifdef PG_PHASE_TIMING
+    return (int)offsetof(EnvHdr, dbg_phase);
+#else
+    return -1;
+#endif
+}
+
 int pgb200_consumer_slot(libenv_env *handle) { return ((VecEnv *)handle)->base.consumer_slot; }
 
 int pgb200_mirror_parity(libenv_env *handle) { return ((VecEnv *)handle)->mirror_parity; }

@@ -144,3 +144,15 @@ def test_unsnapped_target_rect_bit_exact(ref_lib, hostsim_lib):
     from helpers import run_snap_off_lockstep
 
     run_snap_off_lockstep(hostsim_lib)
+
+
+@pytest.mark.parametrize("name", ALL_GAMES.split(","))
+def test_restrict_themes_all_games(ref_lib, hostsim_lib, name):
+    """restrict_themes masks the theme inside initialize_asset_if_necessary (basic-abstract-game.cpp:86), so
+    it changes the aspect ratios game LOGIC reads (match_aspect_ratio / fit_aspect_ratio), not only the
+    sprites drawn — every game, because each has its own multi-theme types."""
+    ref, dut = make_pair(hostsim_lib, 8, name, distribution_mode="hard", num_levels=200, start_level=0, rand_seed=0,
+                         restrict_themes=True)
+    run_lockstep(ref, dut, 150)
+    ref.close()
+    dut.close()
