@@ -14,7 +14,9 @@ struct KParams {
     MT19937 *rng;
     MT19937 *lvl_rng;
     int32_t *scratch;
-    RotBlit *rot_scratch;       // [N][rot_stride] rotated-sprite records of frames too big for shared memory (may be null)
+    RotBlit *rot_scratch;       // [N][rot_stride] rotated-sprite / span records
+    Blit *blit_list;            // [N][blit_stride] background-less blit lists (entities in draw order, then overlays)
+    unsigned char *frame_setup; // [N][frame_setup_stride bytes] FrameSetupT of the env's game
     const GameAssets *assets;   // table of the game this launch handles
     const uint32_t *atlas;
     TileTable tiles;            // pre-scaled cell tiles of every sprite (texels == nullptr: disabled)
@@ -32,6 +34,8 @@ struct KParams {
     int32_t grid_stride;
     int32_t scratch_stride;
     int32_t rot_stride;
+    int32_t blit_stride;
+    int32_t frame_setup_stride;
     // which envs this launch covers: env = env_first + i * env_step, i in [0, env_count)
     int32_t env_first, env_step, env_count;
     // construction-time options (game.cpp:42-75, vecgame.cpp:284-293)
@@ -47,16 +51,8 @@ struct KParams {
     const uint16_t *consumer_lut;  // [256] = (16-bit float)(v / 255.f)
     int32_t consumer_k;         // frames per stack; slots = k == 1 ? 1 : 2k
     int32_t consumer_slot;      // ring position this step writes: t mod k
-    // level generation as its own pass (see pg_launch.cuh): envs whose episode ended this step
-    int32_t *reset_list;        // this launch's segment: env indices, filled by the logic kernel
-    unsigned int *reset_count;  // entries in reset_list (null: resets run inline in the logic kernel)
-    int32_t *reset_epoch;       // [N] step id at which the env last entered a reset list
-    int32_t step_id;
-    int32_t render_mode;        // RENDER_ALL | RENDER_SKIP_RESET (envs listed this step are left to the tail launch) | RENDER_LISTED
     uint32_t *dbg_cycles;       // optional [N] per-env logic duration in SM cycles (profiling aid)
 };
-
-enum RenderMode : int32_t { RENDER_ALL = 0, RENDER_SKIP_RESET = 1, RENDER_LISTED = 2 };
 
 PG_HD Ctx make_ctx(const KParams &p, int env) {
     Ctx c;
@@ -72,6 +68,7 @@ PG_HD Ctx make_ctx(const KParams &p, int env) {
     c.scratch_cap = p.scratch_stride;
     c.obst_hi = -1;
     c.rot_scratch_raw = (p.rot_scratch && p.rot_stride > 0) ? (void *)(p.rot_scratch + (size_t)env * p.rot_stride) : nullptr;
+    c.blit_list = p.blit_list ? p.blit_list + (size_t)env * p.blit_stride : nullptr;
     ctx_refresh(c);
     return c;
 }
@@ -146,48 +143,51 @@ __device__ __forceinline__ void env_prefetch(const KParams &p, int env) {
 #endif
 
 // Game::step (game.cpp:120-155) up to, not including, the pixel work. One thread.
-// SPLIT: level generation is left to the reset pass (the code of reset() is then not even part of
-// the kernel that steps the envs, which keeps it within reach of the instruction cache)
-template <class G, class Frame, bool SPLIT>
+template <class G, class Frame>
 PG_HD void env_step_logic(const KParams &p, int env) {
 #if defined(__CUDA_ARCH__)
     env_prefetch(p, env);
 #endif
     Ctx c = make_ctx(p, env);
     c.h->action = p.action[env];  // vecgame.cpp:388
-    const bool ended = Engine<G>::step_play(c);
-    if (SPLIT && ended) {
-        // level generation runs in the reset pass; it also finishes the step there
-#if defined(__CUDA_ARCH__)
-        if ((threadIdx.x & 31u) == 0) {
-            const unsigned slot = atomicAdd(p.reset_count, 1u);
-            p.reset_list[slot] = env;
-            p.reset_epoch[env] = p.step_id;
-        }
-#else
-        p.reset_list[(*p.reset_count)++] = env;
-        p.reset_epoch[env] = p.step_id;
-#endif
-        return;
-    }
-    Engine<G>::step_finish(c, SPLIT ? false : ended);
+    Engine<G>::step(c);
     Raster<G, Frame>::prepare_camera(c);
     write_step_outputs(p, env, *c.h);
 }
 
-// the second half of Game::step for an env whose episode ended: reset() = level generation
-template <class G, class Frame>
-PG_HD void env_reset_logic(const KParams &p, int env) {
+// ---- setup kernel body: one warp (lanes `lane` of `nlanes`) prepares everything about env's frame that
+// does not depend on pixels or cells: camera, spans, background / overlay / entity blits
+template <class G, class Setup>
+PG_HD void env_setup_frame(const KParams &p, int env, Setup &f, int lane, int nlanes) {
     Ctx c = make_ctx(p, env);
-    Engine<G>::step_finish(c, true);
-    Raster<G, Frame>::prepare_camera(c);
-    write_step_outputs(p, env, *c.h);
+    using R = Raster<G, Setup>;
+    R::setup_frame(c, f, p.snap != 0, lane, nlanes);
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    R::build_entity_blits(c, f, lane, nlanes);
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    if (f.n_jobs > 0) {
+        R::frame_tiles(c, f, lane, nlanes);
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
+    if (G::DEFER_ROTATED) {
+        R::frame_rots(c, f, lane, nlanes);
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
+    if (lane == 0)
+        R::frame_append_overlays(f);
 }
 
 template <class G, class Frame>
 PG_HD void env_render_begin(const KParams &p, int env, Frame &f, int tid, int nthreads) {
-    Ctx c = make_ctx(p, env);
-    Raster<G, Frame>::frame_begin(c, f, p.snap != 0, tid, nthreads);
+    Raster<G, Frame>::render_begin(f, tid, nthreads);
 }
 
 template <class G, class Frame>
@@ -196,25 +196,11 @@ PG_HD void env_render_build(const KParams &p, int env, Frame &f, int tid, int nt
     Raster<G, Frame>::frame_build(c, f, tid, nthreads, ent_group);
 }
 
-// tile registration results -> arena space + staging jobs; tiles of tiled entities; deferred
-// rotated sprites. Independent of each other, so they share one barrier interval.
+// tile registration results -> arena space + staging jobs
 template <class G, class Frame>
 PG_HD void env_render_jobs(const KParams &p, int env, Frame &f, int tid, int nthreads) {
     Ctx c = make_ctx(p, env);
     Raster<G, Frame>::frame_tile_alloc(c, f, p.tiles, tid, nthreads);
-    if (f.n_jobs > 0)
-        Raster<G, Frame>::frame_tiles(c, f, tid, nthreads);
-    if (G::DEFER_ROTATED) {
-#if defined(__CUDA_ARCH__)
-        // frame_rots scans the whole list for reserved slots; the slots frame_tiles fills hold stale
-        // bytes until it has written them (block-uniform condition)
-        if (f.n_jobs > 0)
-            __syncthreads();
-#endif
-        Raster<G, Frame>::frame_rots(c, f, tid, nthreads);
-    }
-    if (tid == nthreads - 1)
-        Raster<G, Frame>::frame_append_overlays(f);
 }
 
 template <class G, class Frame>
@@ -255,6 +241,8 @@ PG_HD void tile_table_fill(const SpriteDesc *sprites, const uint32_t *index, uin
 template <class G>
 struct FrameFor {
     using type = FrameT<(G::DRAWS_GRID ? G::MAX_VIEW_CELLS : 1), G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
+    using setup = FrameSetupT<(G::DRAWS_GRID ? G::MAX_VIEW_CELLS : 1), G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
+    using shared = typename type::Shared;
 };
 
 }  // namespace pg

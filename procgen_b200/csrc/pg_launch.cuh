@@ -69,7 +69,7 @@ constexpr int kRenderThreads = 128;
 // Persistent: the grid is sized to fill the machine once and every warp pulls env indices from a
 // global ticket counter until the launch's range is exhausted, so a long env (level reset) only
 // delays its own warp and no SM slot idles waiting for a block launch.
-template <class G, bool INIT, bool SPLIT>
+template <class G, bool INIT>
 __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kernel(KParams p, unsigned int *ticket) {
     using Frame = typename FrameFor<G>::type;
     const unsigned lane = threadIdx.x & 31u;
@@ -85,36 +85,28 @@ __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kern
         if (INIT)
             env_init_logic<G, Frame>(p, env);
         else
-            env_step_logic<G, Frame, SPLIT>(p, env);
+            env_step_logic<G, Frame>(p, env);
         __syncwarp();
         if (p.dbg_cycles && lane == 0)
             p.dbg_cycles[env] = (uint32_t)(clock64() - t0);
     }
 }
 
-// Level generation pass: the envs whose episode ended in the logic kernel just before (reset_list),
-// one warp each. Its launch is sized for the SM count, not for the list: a reset is one long serial
-// chain (RNG-driven generators), and a warp that has an SM sub-partition to itself runs it at the
-// latency of the chain instead of sharing issue slots with dozens of stepping warps.
+// Frame setup: one warp per env (4 envs per block). Everything about a frame that is O(entities +
+// cell columns): camera, visible window, per-column / per-row pixel spans, background, overlay and
+// entity blits (incl. the scan conversion of rotated sprites). Every warp of the grid runs this
+// same code, which is what the instruction cache wants; the render kernel that follows — one CTA
+// per env — is left with the O(pixels + cells) work and picks the result up with one bulk copy.
+constexpr int kSetupThreads = 128;
 template <class G>
-__global__ void __launch_bounds__(32) reset_kernel(KParams p, unsigned int *ticket) {
-    using Frame = typename FrameFor<G>::type;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned count = *p.reset_count;
-    while (true) {
-        unsigned t = 0;
-        if (lane == 0)
-            t = atomicAdd(ticket, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= count)
-            break;
-        const int env = p.reset_list[t];
-        const long long t0 = p.dbg_cycles ? clock64() : 0;
-        env_reset_logic<G, Frame>(p, env);
-        __syncwarp();
-        if (p.dbg_cycles && lane == 0)
-            p.dbg_cycles[env] += (uint32_t)(clock64() - t0);
-    }
+__global__ void __launch_bounds__(kSetupThreads) setup_kernel(KParams p) {
+    using Setup = typename FrameFor<G>::setup;
+    const int i = (int)blockIdx.x * (kSetupThreads / 32) + (int)(threadIdx.x >> 5);
+    if (i >= p.env_count)
+        return;
+    const int env = p.env_first + i * p.env_step;
+    Setup &f = *reinterpret_cast<Setup *>(p.frame_setup + (size_t)env * p.frame_setup_stride);
+    env_setup_frame<G, Setup>(p, env, f, (int)(threadIdx.x & 31u), 32);
 }
 
 #ifndef PG_RENDER_CTAS_PER_SM
@@ -171,7 +163,8 @@ __device__ __forceinline__ void pg_bulk_store_and_wait(void *dst_gmem, const voi
 }
 
 // One CTA renders one env's frame:
-//   begin / build / jobs   the blit lists, the cell map and the list of pre-scaled tiles the frame needs
+//   begin                  stage what the setup kernel prepared (spans, background, counts) with one bulk copy
+//   build / jobs           the cell map and the list of pre-scaled tiles the frame needs
 //   stage                  warp 0 arms the mbarrier and queues one bulk copy per tile (global table -> shared)
 //   cells                  meanwhile: the cells learn where their tiles are
 //   compose                warp w owns rows y = w (mod 4): gather (cells over background; a lane = 4 pixel
@@ -182,14 +175,7 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     using Frame = typename FrameFor<G>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Frame &f = *reinterpret_cast<Frame *>(smem_raw);
-    int env = p.env_first + (int)blockIdx.x * p.env_step;
-    if (p.render_mode == RENDER_LISTED) {  // the tail launch: envs that went through the reset pass
-        if (blockIdx.x >= *p.reset_count)
-            return;
-        env = p.reset_list[blockIdx.x];
-    } else if (p.render_mode == RENDER_SKIP_RESET && p.reset_epoch[env] == p.step_id) {
-        return;  // being regenerated right now; the tail launch draws it
-    }
+    const int env = p.env_first + (int)blockIdx.x * p.env_step;
     const int tid = (int)threadIdx.x;
 #ifdef PG_PHASE_TIMING
     long long t0 = clock64(), t1;
@@ -203,10 +189,16 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
 #else
 #define PG_RENDER_PHASE(id) do { } while (0)
 #endif
-    if (tid == 0)
+    using Shared = typename FrameFor<G>::shared;
+    if (tid == 0) {
+        // what the setup kernel prepared for this env: one bulk copy into the head of the frame
         pg_mbar_init(&f.mbar, 1);
+        pg_mbar_arrive_expect_tx(&f.mbar, (unsigned)sizeof(Shared));
+        pg_bulk_load(static_cast<Shared *>(&f), p.frame_setup + (size_t)env * p.frame_setup_stride, (unsigned)sizeof(Shared), &f.mbar);
+    }
     env_render_begin<G, Frame>(p, env, f, tid, kRenderThreads);
-    __syncthreads();
+    __syncthreads();   // mbarrier initialised + counters cleared
+    pg_mbar_wait(&f.mbar, 0);
     PG_RENDER_PHASE(0);
     env_render_build<G, Frame>(p, env, f, tid, kRenderThreads, 32);
     __syncthreads();
@@ -228,7 +220,7 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
     __syncthreads();
     PG_RENDER_PHASE(3);
     if (G::DRAWS_GRID)
-        pg_mbar_wait(&f.mbar, 0);
+        pg_mbar_wait(&f.mbar, 1);
     PG_RENDER_PHASE(4);
     // warp w owns rows y = w (mod warps): gather and paint need no block barrier in between
     env_render_compose<G, Frame>(p, f, tid >> 5, kRenderThreads >> 5, tid & 31, 32);
@@ -303,9 +295,14 @@ __global__ void camera_kernel(KParams p) {
 }
 #endif
 
-// the render kernel's phases as plain loops (host debug harness; also documents the phase order)
+// the setup + render kernels' phases as plain loops (host debug harness; also documents the phase order)
 template <class G, class Frame>
 void render_env_serial(const KParams &p, int env, Frame &f) {
+    using Setup = typename FrameFor<G>::setup;
+    using Shared = typename FrameFor<G>::shared;
+    Setup &s = *reinterpret_cast<Setup *>(p.frame_setup + (size_t)env * p.frame_setup_stride);
+    env_setup_frame<G, Setup>(p, env, s, 0, 1);
+    static_cast<Shared &>(f) = static_cast<const Shared &>(s);
     env_render_begin<G, Frame>(p, env, f, 0, 1);
     env_render_build<G, Frame>(p, env, f, 0, 1, 1);
     env_render_jobs<G, Frame>(p, env, f, 0, 1);
@@ -325,9 +322,6 @@ struct LaunchCtx {
     int max_logic_blocks;     // SM count x resident CTAs per SM
     int render_smem_floor;    // dynamic shared memory requested per render CTA is at least this (co-residency knob)
     cudaEvent_t *tev;         // optional: 3 events (before logic, between, after render) for kernel timing
-    cudaStream_t reset_stream;  // null: level generation stays inline in the logic kernel; else the stream of the reset pass
-    cudaEvent_t ev_logic, ev_reset;
-    int reset_blocks;         // grid of the reset kernel (1 warp per block)
 #endif
     int64_t *launch_counter;
 };
@@ -367,73 +361,33 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     if (logic_blocks > lc.max_logic_blocks)
         logic_blocks = lc.max_logic_blocks;
     cudaStream_t ls = lc.logic_stream ? lc.logic_stream : lc.stream;
-    // lc.ticket = this launch slot's 4 counters: [0] logic tickets, [1] reset-list length, [2] reset tickets
-    CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, 4 * sizeof(unsigned int), ls));
+    CUDA_CHECK(cudaMemsetAsync(lc.ticket, 0, sizeof(unsigned int), ls));
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[0], ls));
-    KParams q = p;
-    const bool split = !INIT && p.reset_list != nullptr;
-    q.reset_count = split ? lc.ticket + 1 : nullptr;
-    q.render_mode = RENDER_ALL;
-    if (split)
-        logic_kernel<G, false, true><<<logic_blocks, kLogicThreads, 0, ls>>>(q, lc.ticket);
-    else
-        logic_kernel<G, INIT, false><<<logic_blocks, kLogicThreads, 0, ls>>>(q, lc.ticket);
+    logic_kernel<G, INIT><<<logic_blocks, kLogicThreads, 0, ls>>>(p, lc.ticket);
     if (lc.logic_stream) {
         CUDA_CHECK(cudaEventRecord(lc.link, ls));
         CUDA_CHECK(cudaStreamWaitEvent(lc.stream, lc.link, 0));
     }
-    int launches = 2;
-    if (split && lc.reset_stream) {
-        // level generation next to the rendering of everybody else: reset kernel + the tail render
-        // launch of the regenerated envs on the reset stream, the main render launch skips them
-        CUDA_CHECK(cudaEventRecord(lc.ev_logic, lc.stream));
-        CUDA_CHECK(cudaStreamWaitEvent(lc.reset_stream, lc.ev_logic, 0));
-        reset_kernel<G><<<lc.reset_blocks, 32, 0, lc.reset_stream>>>(q, lc.ticket + 2);
-        KParams qt = q;
-        qt.render_mode = RENDER_LISTED;
-        render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.reset_stream>>>(qt);
-        CUDA_CHECK(cudaEventRecord(lc.ev_reset, lc.reset_stream));
-        q.render_mode = RENDER_SKIP_RESET;
-        if (lc.tev)
-            CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
-        render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(q);
-        if (lc.tev)
-            CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
-        CUDA_CHECK(cudaStreamWaitEvent(lc.stream, lc.ev_reset, 0));
-        launches = 4;
-    } else {
-        if (split) {
-            reset_kernel<G><<<lc.reset_blocks, 32, 0, lc.stream>>>(q, lc.ticket + 2);
-            launches = 3;
-        }
-        if (lc.tev)
-            CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
-        render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(q);
-        if (lc.tev)
-            CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
-    }
+    if (lc.tev)
+        CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
+    setup_kernel<G><<<(p.env_count + kSetupThreads / 32 - 1) / (kSetupThreads / 32), kSetupThreads, 0, lc.stream>>>(p);
+    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
+    if (lc.tev)
+        CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
     CUDA_CHECK(cudaGetLastError());
-    (*lc.launch_counter) += launches;
+    (*lc.launch_counter) += 3;
 #else
     static thread_local Frame *f = new Frame;
-    // the device's three passes in order: step logic, level generation of the envs it listed, frames
-    KParams q = p;
-    unsigned int n_reset = 0;
-    q.reset_count = (!INIT && p.reset_list != nullptr) ? &n_reset : nullptr;
-    q.render_mode = RENDER_ALL;
     for (int b = 0; b < p.env_count; b++) {
         int env = p.env_first + b * p.env_step;
         if (INIT)
-            env_init_logic<G, Frame>(q, env);
-        else if (q.reset_count)
-            env_step_logic<G, Frame, true>(q, env);
+            env_init_logic<G, Frame>(p, env);
         else
-            env_step_logic<G, Frame, false>(q, env);
+            env_step_logic<G, Frame>(p, env);
+        render_env_serial<G, Frame>(p, env, *f);
     }
-    for (unsigned t = 0; t < n_reset; t++) env_reset_logic<G, Frame>(q, q.reset_list[t]);
-    for (int b = 0; b < p.env_count; b++) render_env_serial<G, Frame>(q, p.env_first + b * p.env_step, *f);
-    (*lc.launch_counter) += 2;
+    (*lc.launch_counter) += 3;
 #endif
 }
 
@@ -445,9 +399,8 @@ void launch_observe_only(const KParams &p, const LaunchCtx &lc) {
 #ifndef PG_HOSTSIM
     const int render_smem = prepare_render_smem<G>(lc);
     camera_kernel<G><<<p.env_count, 32, 0, lc.stream>>>(p);
-    KParams q = p;
-    q.render_mode = RENDER_ALL;
-    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(q);
+    setup_kernel<G><<<(p.env_count + kSetupThreads / 32 - 1) / (kSetupThreads / 32), kSetupThreads, 0, lc.stream>>>(p);
+    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
 #else
     static thread_local Frame *f = new Frame;
@@ -466,7 +419,9 @@ struct GameVTable {
     const char *name;
     int id;
     int ent_cap, grid_cap, scratch_words;
-    int rot_records;  // rotated-sprite records kept in global memory per env (0 = the frame holds them)
+    int rot_records;  // rotated-sprite / span records per env (global)
+    int blit_records; // blit list capacity per env (global)
+    int setup_bytes;  // sizeof(FrameSetupT) of the game
     int frame_bytes;  // shared memory of one render CTA
     int render_ctas_per_sm;  // residency the render kernel is compiled for
     void (*init)(const KParams &, const LaunchCtx &);
@@ -476,7 +431,7 @@ struct GameVTable {
 
 template <class G>
 GameVTable make_vtable(int id) {
-    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, FrameFor<G>::type::kRotInGlobal ? G::MAX_ROT_BLITS : 0,
+    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, FrameFor<G>::type::kMaxRot, FrameFor<G>::type::kMaxList, (int)sizeof(typename FrameFor<G>::setup),
                       (int)sizeof(typename FrameFor<G>::type),
 #ifndef PG_HOSTSIM
                       RenderTune<G>::kMinBlocks,

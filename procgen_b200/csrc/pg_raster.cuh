@@ -96,25 +96,17 @@ constexpr int CI_D_SHIFT = 11;                   // 5 bits: px - col_p1 (py - ro
 constexpr int CI_TW_SHIFT = 16;                  // 5 bits, column only: row stride of its tiles (0: not tile-eligible)
 constexpr uint32_t CI_MULTI = 1u << 21;          // more than one cell column / row covers the pixel
 
+// One frame's working set, in three parts:
+//   FrameSharedT  what the setup kernel (one warp per env: camera, cell spans, background and entity
+//                 blits — everything that is O(entities + cell columns) and heavy on fp64) hands to the
+//                 render kernel. Lives in global memory; the render CTA stages it into its shared
+//                 memory with one bulk copy.
+//   FrameSetupT   + the setup kernel's own scratch (global, per env)
+//   FrameT        + the render kernel's scratch (shared memory): frame buffer, tile arena, cell map
 template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
-struct FrameT {
+struct alignas(16) FrameSharedT {
     static constexpr int kMaxCells1D = MAX_CELLS_1D;
     static constexpr int kMaxRot = MAX_ROT_BLITS > 0 ? MAX_ROT_BLITS : 1;
-    // Frames of bullet-heavy games would spend most of their shared memory on rotated-sprite
-    // records (208 B each) and fit only 2-3 times per SM; above 32 records they live in the env's
-    // slice of a global scratch array instead (L1/L2 resident while the CTA works on the frame).
-    static constexpr bool kRotInGlobal = MAX_ROT_BLITS > 32;
-    // ---- 16-byte aligned blocks first (bulk-copy targets / sources)
-    // the frame as 0xFFRRGGBB pixels while it is composed; packed to RGB888 in place (its first
-    // 12 KiB) and written out with one bulk store
-    alignas(16) uint32_t fb[RES_W * RES_H];
-    // tiles (texels, growing up from word 0) and general cell blits (32 B each, growing down from the end)
-    static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 8;
-    alignas(16) uint32_t arena[kArenaWords];
-    alignas(8) unsigned long long mbar;   // tile staging barrier
-    int32_t n_rot;
-    RotBlit *rot;
-    RotBlit rot_local[kRotInGlobal ? 1 : kMaxRot];
     // `ents` = VISIBLE entity blits (after culling) in draw order, then the overlay blits (drawn last)
     static constexpr int kMaxEntBlits = MAX_ENT_BLITS;
     static constexpr int kMaxList = MAX_ENT_BLITS + MAX_OVERLAY_BLITS;
@@ -122,19 +114,48 @@ struct FrameT {
     int32_t low_x, low_y, nx, ny;   // visible grid window: cells [low_x, low_x+nx) x [low_y, low_y+ny)
     int32_t n_bg, n_ent, n_ent_below, n_overlay;  // n_ent_below = entities with render_z == -1
     int32_t snap;
-    int32_t pad;                    // 1: the background is one opaque un-mirrored image (bgrow[] valid; it may cover only part of the device)
+    int32_t pad;                    // 1: the background is one opaque un-mirrored image (it may cover only part of the device)
     int32_t tile_w0, tile_h0;       // smaller of the two snapped cell sizes of this frame
-    int32_t n_gen;                  // general cell blits in use
-    int32_t tile_top;               // arena words used by tiles
-    int32_t n_tjobs;
+    int32_t n_rot;
+    int32_t spare[3];
+    RotBlit *rot;                   // this env's rotated-sprite / span records (global)
+    Blit *ents;                     // this env's blit list (global): the painter reads it sequentially
     // geometry shared by all cells of a column / row (the cell rect is separable)
+    double cell_w;                  // QRectF.width == height
+    double spare_d;
     double col_x[MAX_CELLS_1D];     // QRectF.x of column i
     double row_y[MAX_CELLS_1D];     // QRectF.y of row j
-    double cell_w;                  // QRectF.width == height
     uint8_t col_p1[MAX_CELLS_1D], col_p2[MAX_CELLS_1D];  // device pixel span [p1,p2) of column i
     uint8_t row_p1[MAX_CELLS_1D], row_p2[MAX_CELLS_1D];
     uint8_t col_tw[MAX_CELLS_1D], row_th[MAX_CELLS_1D];  // snapped size if the column / row can use tiles, else 0
     uint8_t col_k0[MAX_CELLS_1D], row_k0[MAX_CELLS_1D];  // pixels the device edge cuts off the near side (tile offset of the first visible one)
+    Blit bg[MAX_BG_BLITS];
+};
+
+template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
+struct alignas(16) FrameSetupT : FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_ROT_BLITS> {
+    using Shared = FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_ROT_BLITS>;
+    // tiled entities only reserve their blit slots while the list is built; the tiles themselves
+    // are filled in by all lanes afterwards (frame_tiles)
+    static constexpr int kMaxTileJobs = 64;
+    int32_t n_jobs;
+    int32_t job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs], job_j0[kMaxTileJobs];
+    Blit overlay[MAX_OVERLAY_BLITS];
+};
+
+template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
+struct alignas(16) FrameT : FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_ROT_BLITS> {
+    using Shared = FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_ROT_BLITS>;
+    // the frame as 0xFFRRGGBB pixels while it is composed; packed to RGB888 in place (its first
+    // 12 KiB) and written out with one bulk store
+    alignas(16) uint32_t fb[RES_W * RES_H];
+    // tiles (texels, growing up from word 0) and general cell blits (32 B each, growing down from the end)
+    static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 8;
+    alignas(16) uint32_t arena[kArenaWords];
+    alignas(8) unsigned long long mbar;   // staging barrier: phase 0 the shared part, phase 1 the tiles
+    int32_t n_gen;                  // general cell blits in use
+    int32_t tile_top;               // arena words used by tiles
+    int32_t n_tjobs;
     int32_t n_strip_cols;                                // pixel columns where two cell columns overlap
     uint8_t strip_cols[RES_W];
     uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
@@ -145,14 +166,6 @@ struct FrameT {
     alignas(4) uint16_t tilekey[MAX_CELLS_1D > 1 ? CELL_KEYS : 4];  // per (type, size variant): 0 unused | 1 wanted | 2 + arena texel offset | 0xffff unavailable
     uint32_t tjob_src[MAX_TILE_JOBS];         // tile copies to stage: texel offset in the table,
     uint16_t tjob_dst[MAX_TILE_JOBS], tjob_words[MAX_TILE_JOBS];  // arena word offset, words
-    // tiled entities only reserve their blit slots while the list is built; the tiles themselves
-    // are filled in by all threads afterwards (frame_tiles)
-    static constexpr int kMaxTileJobs = 64;
-    int32_t n_jobs;
-    int32_t job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs], job_j0[kMaxTileJobs];
-    Blit bg[MAX_BG_BLITS];
-    Blit overlay[MAX_OVERLAY_BLITS];
-    Blit ents[kMaxList];
 
     PG_HD Blit *gen_blit(int k) { return reinterpret_cast<Blit *>(arena + kArenaWords) - 1 - k; }
     PG_HD const Blit *gen_blit(int k) const { return reinterpret_cast<const Blit *>(arena + kArenaWords) - 1 - k; }
@@ -1151,8 +1164,10 @@ struct Raster {
         p2 = (uint8_t)b2;
     }
 
-    // ---- phase B
-    static PG_HD void frame_begin(Ctx &c, Frame &f, bool snap, int tid, int nthreads) {
+    // ---- setup kernel, step 1: camera, visible window, background + overlay blits, cell spans
+    // (prepare_for_drawing's results are in the header already; this is draw_background's and
+    // draw_foreground's geometry, basic-abstract-game.cpp:921-1007). `tid` of `nthreads` lanes of one warp.
+    static PG_HD void setup_frame(Ctx &c, Frame &f, bool snap, int tid, int nthreads) {
         EnvHdr &h = *c.h;
         const Camera cam = camera_of(h);
         int low_x, low_y, nx, ny;
@@ -1184,16 +1199,10 @@ struct Raster {
             f.n_ent_below = 0;
             f.n_rot = 0;
             f.n_jobs = 0;
-            f.n_gen = 0;
-            f.tile_top = 0;
-            f.n_tjobs = 0;
-            f.n_strip_cols = 0;
             f.tile_w0 = f.tile_h0 = w0;
-            f.rot = Frame::kRotInGlobal ? reinterpret_cast<RotBlit *>(c.rot_scratch_raw) : f.rot_local;
-            if (Frame::kRotInGlobal && c.rot_scratch_raw == nullptr) {
-                h.err |= ERR_SCRATCH_OVERFLOW;
-                f.rot = f.rot_local;
-            }
+            f.cell_w = cw[2];
+            f.rot = reinterpret_cast<RotBlit *>(c.rot_scratch_raw);
+            f.ents = c.blit_list;
             if (overflow)
                 h.err |= ERR_BLIT_OVERFLOW;
             if (h.options.use_backgrounds)
@@ -1224,17 +1233,11 @@ struct Raster {
             }
             G::make_overlay_blits(c, f);  // game overlays are appended after the velocity squares
         }
-        if (G::DRAWS_GRID) {
-            uint32_t *keys = reinterpret_cast<uint32_t *>(f.tilekey);
-            for (int i = tid; i < CELL_KEYS / 2; i += nthreads) keys[i] = 0;
-        }
-        // columns by threads 0.., rows by threads from the top end so they land on other lanes
+        // columns by lanes 0.., rows by lanes from the top end
         for (int i = tid; i < nx; i += nthreads) {
             double r[4];
             screen_rect(cam, (float)(low_x + i), (float)(low_y + 1), 1, 1, RENDER_EPS, r);
             f.col_x[i] = r[0];
-            if (i == 0)
-                f.cell_w = r[2];
             uint8_t ts;
             span_of(r[0], r[2], snap, RES_W, f.col_p1[i], f.col_p2[i], ts, f.col_k0[i]);
             f.col_tw[i] = (ts == w0 || ts == w0 + 1) ? ts : 0;
@@ -1247,6 +1250,20 @@ struct Raster {
             uint8_t ts;
             span_of(r[1], r[3], snap, RES_H, f.row_p1[j], f.row_p2[j], ts, f.row_k0[j]);
             f.row_th[j] = (ts == w0 || ts == w0 + 1) ? ts : 0;
+        }
+    }
+
+    // ---- render kernel, phase B: its own counters and the tile registration table
+    static PG_HD void render_begin(Frame &f, int tid, int nthreads) {
+        if (tid == 0) {
+            f.n_gen = 0;
+            f.tile_top = 0;
+            f.n_tjobs = 0;
+            f.n_strip_cols = 0;
+        }
+        if (G::DRAWS_GRID) {
+            uint32_t *keys = reinterpret_cast<uint32_t *>(f.tilekey);
+            for (int i = tid; i < CELL_KEYS / 2; i += nthreads) keys[i] = 0;
         }
     }
 
@@ -1540,21 +1557,9 @@ struct Raster {
         return true;
     }
 
-    // ---- phase C. Few entities: warp 0 builds the entity list while the other warps classify the
-    // cells and build the pixel -> cell lookups. Many entities (bullet-heavy frames, tiled walls):
-    // the whole CTA builds the list, then the cells.
+    // ---- render kernel, phase C: pixel -> cell lookups and the first pass over the visible cells
     static PG_HD void frame_build(Ctx &c, Frame &f, int tid, int nthreads, int /*unused*/) {
-        int wtid = tid, wn = nthreads;
-        if (nthreads > 32 && c.h->n_ents <= 32) {
-            if (tid < 32) {
-                build_entity_blits(c, f, tid, 32);
-                return;
-            }
-            wtid = tid - 32;
-            wn = nthreads - 32;
-        } else {
-            build_entity_blits(c, f, tid, nthreads);
-        }
+        const int wtid = tid, wn = nthreads;
         if (f.pad == 1) {
             const Blit &b = f.bg[0];
             for (int py = wtid; py < RES_H; py += wn) {

@@ -247,17 +247,8 @@ struct VecEnv {
     static constexpr int kChunks = PG_STEP_CHUNKS;
     int force_chunks = 0;            // measurement knobs (pgb200_set_launch_shape)
     bool serialize_launches = false;
-    static constexpr int kMaxTickets = 64;   // launch slots in flight; 4 counters each (logic tickets, reset-list length, reset tickets)
+    static constexpr int kMaxTickets = 64;   // launch slots in flight (one ticket counter each)
     unsigned int *d_tickets = nullptr;
-    // level generation as its own pass: per-launch lists of the envs whose episode just ended
-    bool split_reset = true;
-    int32_t *d_reset_list = nullptr, *d_reset_epoch = nullptr;
-    int32_t step_id = 0;
-    int reset_blocks = 1;
-#ifndef PG_HOSTSIM
-    cudaStream_t aux_reset[PG_AUX_STREAMS] = {};
-    cudaEvent_t ev_logic[kMaxTickets] = {}, ev_reset[kMaxTickets] = {};
-#endif
     int max_logic_blocks = 1 << 30;
     int render_smem_floor = 0;
     // host-buffer (libenv) mode
@@ -294,9 +285,6 @@ struct VecEnv {
         lc.max_logic_blocks = max_logic_blocks;
         lc.render_smem_floor = render_smem_floor;
         lc.tev = nullptr;
-        lc.reset_stream = nullptr;
-        lc.ev_logic = lc.ev_reset = nullptr;
-        lc.reset_blocks = reset_blocks;
 #endif
         lc.launch_counter = &launches;
         return lc;
@@ -327,8 +315,6 @@ struct VecEnv {
 #endif
         if (!init && mirror[0])
             mirror_parity ^= 1;
-        if (!init)
-            step_id++;
         if (!init && base.consumer) {
             consumer_steps++;
             base.consumer_slot = (int32_t)(consumer_steps % base.consumer_k);
@@ -345,9 +331,6 @@ struct VecEnv {
                 p.env_first = g + lo * G;
                 p.env_step = G;
                 p.env_count = hi - lo;
-                p.step_id = step_id;
-                p.reset_epoch = d_reset_epoch;
-                p.reset_list = (split_reset && !init) ? d_reset_list + ((size_t)g * per_game + lo) : nullptr;
                 LaunchCtx lc = lctx();
 #ifndef PG_HOSTSIM
                 if (nstreams) {
@@ -357,13 +340,7 @@ struct VecEnv {
                         lc.link = ev_link[k % nstreams];
                     }
                 }
-                lc.ticket = d_tickets + 4 * (k % kMaxTickets);
-                if (nstreams && split_reset && !init) {
-                    // the reset pass of this launch runs beside its (and everybody's) main render launch
-                    lc.reset_stream = aux_reset[k % nstreams];
-                    lc.ev_logic = ev_logic[k % kMaxTickets];
-                    lc.ev_reset = ev_reset[k % kMaxTickets];
-                }
+                lc.ticket = d_tickets + (k % kMaxTickets);
                 if (timing && tev_used + 3 <= tev_pool.size()) {
                     lc.tev = &tev_pool[tev_used];
                     tev_used += 3;
@@ -624,14 +601,7 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
             v->render_smem_floor = (227 * 1024) / render_ctas - 1024 - 16;
             v->render_smem_floor &= ~15;
         }
-        CUDA_CHECK(cudaMalloc((void **)&v->d_tickets, 4 * VecEnv::kMaxTickets * sizeof(unsigned int)));
-        CUDA_CHECK(cudaMemset(v->d_tickets, 0, 4 * VecEnv::kMaxTickets * sizeof(unsigned int)));
-        v->reset_blocks = prop.multiProcessorCount * 4;
-        for (int s = 0; s < VecEnv::kAuxStreams; s++) CUDA_CHECK(cudaStreamCreateWithFlags(&v->aux_reset[s], cudaStreamNonBlocking));
-        for (int s = 0; s < VecEnv::kMaxTickets; s++) {
-            CUDA_CHECK(cudaEventCreateWithFlags(&v->ev_logic[s], cudaEventDisableTiming));
-            CUDA_CHECK(cudaEventCreateWithFlags(&v->ev_reset[s], cudaEventDisableTiming));
-        }
+        CUDA_CHECK(cudaMalloc((void **)&v->d_tickets, VecEnv::kMaxTickets * sizeof(unsigned int)));
     }
     // sub_step <-> push_obj recurse to depth 5 on the logic thread
     {
@@ -706,9 +676,11 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     fill_tensortypes(v);
 
     // ---- state arrays
-    int ent_cap = 0, grid_cap = 0, scratch_words = 0, rot_records = 0;
+    int ent_cap = 0, grid_cap = 0, scratch_words = 0, rot_records = 0, blit_records = 0, setup_bytes = 0;
     for (auto g : v->games) {
         rot_records = std::max(rot_records, g->rot_records);
+        blit_records = std::max(blit_records, g->blit_records);
+        setup_bytes = std::max(setup_bytes, g->setup_bytes);
         ent_cap = std::max(ent_cap, g->ent_cap);
         grid_cap = std::max(grid_cap, g->grid_cap);
         scratch_words = std::max(scratch_words, g->scratch_words);
@@ -726,6 +698,10 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     p.scratch = dev_alloc<int32_t>(N * (size_t)scratch_words);
     p.rot_stride = rot_records;
     p.rot_scratch = rot_records > 0 ? dev_alloc<RotBlit>(N * (size_t)rot_records) : nullptr;
+    p.blit_stride = blit_records;
+    p.blit_list = dev_alloc<Blit>(N * (size_t)blit_records);
+    p.frame_setup_stride = (setup_bytes + 15) & ~15;
+    p.frame_setup = dev_alloc<unsigned char>(N * (size_t)p.frame_setup_stride);
     p.atlas = v->d_atlas;
     v->d_action = dev_alloc<int32_t>(N);
     p.action = v->d_action;
@@ -736,10 +712,7 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     p.info_prev_level_complete = dev_alloc<uint8_t>(N);
     p.info_level_seed = dev_alloc<int32_t>(N);
     p.dbg_cycles = getenv("PGB200_DEBUG_TIMING") ? dev_alloc<uint32_t>(N) : nullptr;
-    if (const char *e = getenv("PGB200_SPLIT_RESET"))
-        v->split_reset = atoi(e) != 0;
-    v->d_reset_list = dev_alloc<int32_t>(N);
-    v->d_reset_epoch = dev_alloc<int32_t>(N);   // zero-filled; step ids start at 1
+
 
     // ---- per-env seed chain (vecgame.cpp:301-314), replayed for the global env indices
     {
@@ -939,6 +912,8 @@ void libenv_close(libenv_env *handle) {
     dev_free(p.scratch);
     if (p.rot_scratch)
         dev_free(p.rot_scratch);
+    dev_free(p.blit_list);
+    dev_free(p.frame_setup);
     dev_free(v->d_atlas);
     dev_free(v->d_tile_texels);
     dev_free(v->d_tile_index);
@@ -951,8 +926,6 @@ void libenv_close(libenv_env *handle) {
     dev_free(p.info_prev_level_complete);
     dev_free(p.info_level_seed);
     dev_free(v->d_lvl_seeds);
-    dev_free(v->d_reset_list);
-    dev_free(v->d_reset_epoch);
     dev_free(v->d_consumer_lut);
     if (p.dbg_cycles)
         dev_free(p.dbg_cycles);
@@ -962,15 +935,7 @@ void libenv_close(libenv_env *handle) {
 #ifndef PG_HOSTSIM
     if (v->d_tickets)
         cudaFree(v->d_tickets);
-    for (int s = 0; s < VecEnv::kAuxStreams; s++)
-        if (v->aux_reset[s])
-            cudaStreamDestroy(v->aux_reset[s]);
-    for (int s = 0; s < VecEnv::kMaxTickets; s++) {
-        if (v->ev_logic[s])
-            cudaEventDestroy(v->ev_logic[s]);
-        if (v->ev_reset[s])
-            cudaEventDestroy(v->ev_reset[s]);
-    }
+
 #endif
     for (auto a : v->d_assets) dev_free(a);
     host_free(v->st_rgb);

@@ -151,6 +151,7 @@ struct GameAssets {
 };
 
 // Handle a thread uses to reach one env. Pointers are generic (global or shared).
+struct Blit;
 struct Ctx {
     EnvHdr *h;
     Entity *ents;
@@ -162,7 +163,8 @@ struct Ctx {
     int32_t ent_cap;      // list capacity; slot [ent_cap] is the agent ghost slot
     int32_t grid_cap;
     int32_t scratch_cap;  // in int32 words
-    void *rot_scratch_raw; // per-env slice for rotated-sprite records of bullet-heavy frames (render only)
+    void *rot_scratch_raw; // per-env slice for rotated-sprite / span records (setup + render kernels)
+    struct Blit *blit_list; // per-env blit list the setup kernel fills and the render kernel paints
     // register-resident copies of header scalars the physics loop reads constantly; refreshed by
     // ctx_refresh() whenever a game changes them (world size is chosen per episode)
     int32_t mw, mh, oob;
