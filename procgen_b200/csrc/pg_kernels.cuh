@@ -17,6 +17,7 @@ struct KParams {
     RotBlit *rot_scratch;       // [N][rot_stride] rotated-sprite / span records
     Blit *blit_list;            // [N][blit_stride] background-less blit lists (entities in draw order, then overlays)
     unsigned char *frame_setup; // [N][frame_setup_stride bytes] FrameSetupT of the env's game
+    Blit *cell_spill;           // [N][cell_spill_stride] general cell blits that do not fit the render CTA's shared memory
     const GameAssets *assets;   // table of the game this launch handles
     const uint32_t *atlas;
     TileTable tiles;            // pre-scaled cell tiles of every sprite (texels == nullptr: disabled)
@@ -36,6 +37,7 @@ struct KParams {
     int32_t rot_stride;
     int32_t blit_stride;
     int32_t frame_setup_stride;
+    int32_t cell_spill_stride;
     // which envs this launch covers: env = env_first + i * env_step, i in [0, env_count)
     int32_t env_first, env_step, env_count;
     // construction-time options (game.cpp:42-75, vecgame.cpp:284-293)
@@ -187,7 +189,7 @@ PG_HD void env_setup_frame(const KParams &p, int env, Setup &f, int lane, int nl
 
 template <class G, class Frame>
 PG_HD void env_render_begin(const KParams &p, int env, Frame &f, int tid, int nthreads) {
-    Raster<G, Frame>::render_begin(f, tid, nthreads);
+    Raster<G, Frame>::render_begin(f, p.cell_spill ? p.cell_spill + (size_t)env * p.cell_spill_stride : nullptr, tid, nthreads);
 }
 
 template <class G, class Frame>

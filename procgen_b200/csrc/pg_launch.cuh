@@ -422,6 +422,7 @@ struct GameVTable {
     int rot_records;  // rotated-sprite / span records per env (global)
     int blit_records; // blit list capacity per env (global)
     int setup_bytes;  // sizeof(FrameSetupT) of the game
+    int cell_records; // cells of the largest visible window (spill capacity for general cell blits)
     int frame_bytes;  // shared memory of one render CTA
     int render_ctas_per_sm;  // residency the render kernel is compiled for
     void (*init)(const KParams &, const LaunchCtx &);
@@ -432,6 +433,7 @@ struct GameVTable {
 template <class G>
 GameVTable make_vtable(int id) {
     return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, FrameFor<G>::type::kMaxRot, FrameFor<G>::type::kMaxList, (int)sizeof(typename FrameFor<G>::setup),
+                      FrameFor<G>::type::kMaxCells1D * FrameFor<G>::type::kMaxCells1D,
                       (int)sizeof(typename FrameFor<G>::type),
 #ifndef PG_HOSTSIM
                       RenderTune<G>::kMinBlocks,

@@ -83,10 +83,10 @@ struct TileTable {
 };
 PG_HD int tile_words(int tw, int th) { return (tw * th + 3) & ~3; }
 
-constexpr int CELL_KEY_TYPES = 128;              // grid object ids that can use a tile (others take the general path)
+constexpr int CELL_KEY_TYPES = 64;               // grid object ids that can use a tile (others take the general path)
 constexpr int CELL_KEYS = CELL_KEY_TYPES * 4;    // x (tw - W0, th - H0) in {0,1}^2
 constexpr uint16_t CELL_GENERAL = 0x8000u;       // cellmap code: 0 none | 1 + texel offset of its tile in the arena | CELL_GENERAL | blit index
-constexpr int MAX_TILE_JOBS = 96;
+constexpr int MAX_TILE_JOBS = 64;
 constexpr uint32_t BG_NONE = 0xffffffffu;
 
 // colinfo / rowinfo word of a pixel column / row (cells of the visible grid window)
@@ -95,6 +95,7 @@ constexpr uint32_t CI_VALID = 1u << 10;          // some cell column / row cover
 constexpr int CI_D_SHIFT = 11;                   // 5 bits: px - col_p1 (py - row_p1)
 constexpr int CI_TW_SHIFT = 16;                  // 5 bits, column only: row stride of its tiles (0: not tile-eligible)
 constexpr uint32_t CI_MULTI = 1u << 21;          // more than one cell column / row covers the pixel
+constexpr uint32_t CI_FAST = 1u << 22;           // exactly one does
 
 // One frame's working set, in three parts:
 //   FrameSharedT  what the setup kernel (one warp per env: camera, cell spans, background and entity
@@ -149,9 +150,14 @@ struct alignas(16) FrameT : FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_ROT_BL
     // the frame as 0xFFRRGGBB pixels while it is composed; packed to RGB888 in place (its first
     // 12 KiB) and written out with one bulk store
     alignas(16) uint32_t fb[RES_W * RES_H];
-    // tiles (texels, growing up from word 0) and general cell blits (32 B each, growing down from the end)
-    static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 8;
+    // staged tiles (texels); tiles that do not fit turn their cells into general blits
+    static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? (MAX_CELLS_1D * MAX_CELLS_1D * 8 < 1280 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 1280) : 4;
     alignas(16) uint32_t arena[kArenaWords];
+    // general cell blits: the first few here, the rest in the env's global spill slice (frames of
+    // solid-colour cells, un-snapped targets, monochrome mode: every cell is one)
+    static constexpr int kGenSmem = MAX_CELLS_1D > 1 ? 32 : 1;
+    Blit gen_smem[kGenSmem];
+    Blit *gen_spill;
     alignas(8) unsigned long long mbar;   // staging barrier: phase 0 the shared part, phase 1 the tiles
     int32_t n_gen;                  // general cell blits in use
     int32_t tile_top;               // arena words used by tiles
@@ -167,8 +173,8 @@ struct alignas(16) FrameT : FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_ROT_BL
     uint32_t tjob_src[MAX_TILE_JOBS];         // tile copies to stage: texel offset in the table,
     uint16_t tjob_dst[MAX_TILE_JOBS], tjob_words[MAX_TILE_JOBS];  // arena word offset, words
 
-    PG_HD Blit *gen_blit(int k) { return reinterpret_cast<Blit *>(arena + kArenaWords) - 1 - k; }
-    PG_HD const Blit *gen_blit(int k) const { return reinterpret_cast<const Blit *>(arena + kArenaWords) - 1 - k; }
+    PG_HD Blit *gen_blit(int k) { return k < kGenSmem ? gen_smem + k : gen_spill + (k - kGenSmem); }
+    PG_HD const Blit *gen_blit(int k) const { return k < kGenSmem ? gen_smem + k : gen_spill + (k - kGenSmem); }
 };
 
 // ---- rule S: un-rotated scaled image (qt_scale_image_32bit)
@@ -1254,8 +1260,9 @@ struct Raster {
     }
 
     // ---- render kernel, phase B: its own counters and the tile registration table
-    static PG_HD void render_begin(Frame &f, int tid, int nthreads) {
+    static PG_HD void render_begin(Frame &f, Blit *gen_spill, int tid, int nthreads) {
         if (tid == 0) {
+            f.gen_spill = gen_spill;
             f.n_gen = 0;
             f.tile_top = 0;
             f.n_tjobs = 0;
@@ -1271,7 +1278,19 @@ struct Raster {
     static PG_HD uint32_t cell_lookup(const uint8_t *p1, const uint8_t *p2, const uint8_t *tsize, const uint8_t *k0, int n, int base_mul, int px, uint8_t &lo,
                                       uint8_t &hi) {
         int l = 255, hgh = 0;
-        for (int i = 0; i < n; i++) {
+        // spans are monotonic: only the columns around the proportional estimate can cover px
+        // (cell spans differ from the ideal grid by less than a pixel; +-3 also covers 1-pixel cells)
+        int first = 0, last = n - 1;
+        if (n > 8) {
+            const bool reversed = p1[n - 1] < p1[0];  // cell rows run bottom-up: pixel spans decrease with the index
+            const int span0 = reversed ? p1[n - 1] : p1[0], span1 = reversed ? p2[0] : p2[n - 1];
+            int est = span1 > span0 ? ((px - span0) * n) / (span1 - span0) : 0;
+            if (reversed)
+                est = n - 1 - est;
+            first = est - 3 < 0 ? 0 : est - 3;
+            last = est + 3 > n - 1 ? n - 1 : est + 3;
+        }
+        for (int i = first; i <= last; i++) {
             if (px >= p1[i] && px < p2[i]) {
                 if (l == 255) {
                     l = i;
@@ -1282,13 +1301,24 @@ struct Raster {
                 }
             }
         }
+        if (n > 8 && (l == 255 || (l == first && first > 0) || (hgh == last && last < n - 1))) {
+            // nothing found, or a hit on the rim of the window (a neighbour outside it could overlap): scan all
+            l = 255;
+            hgh = 0;
+            for (int i = 0; i < n; i++) {
+                if (px >= p1[i] && px < p2[i]) {
+                    if (l == 255)
+                        l = i;
+                    hgh = i;
+                }
+            }
+        }
         lo = (uint8_t)l;
         hi = (uint8_t)hgh;
         if (l == 255)
             return 0;
         uint32_t w = (uint32_t)(hgh * base_mul) | CI_VALID | ((uint32_t)((px - p1[hgh] + k0[hgh]) & 31) << CI_D_SHIFT) | ((uint32_t)tsize[hgh] << CI_TW_SHIFT);
-        if (l != hgh)
-            w |= CI_MULTI;
+        w |= l != hgh ? CI_MULTI : CI_FAST;
         return w;
     }
 
@@ -1631,6 +1661,10 @@ struct Raster {
             make_sprite_blit(c, f, b, r, 0, false, type, theme, 1.0f);
             if (b.kind == BLIT_NONE)
                 continue;
+            if (slot >= Frame::kGenSmem && f.gen_spill == nullptr) {
+                c.h->err |= ERR_TILE_ARENA;
+                continue;
+            }
             *f.gen_blit(slot) = b;
             f.cellmap[k] = (uint16_t)(CELL_GENERAL | slot);
         }
@@ -1640,7 +1674,6 @@ struct Raster {
     static PG_HD void frame_tile_alloc(Ctx &c, Frame &f, const TileTable &tt, int tid, int nthreads) {
         if (!G::DRAWS_GRID)
             return;
-        const int gen_words = f.n_gen * (int)(sizeof(Blit) / 4);
         for (int key = tid; key < CELL_KEYS; key += nthreads) {
             if (f.tilekey[key] != 1)
                 continue;
@@ -1660,7 +1693,7 @@ struct Raster {
                 off = f.tile_top;
                 f.tile_top += words;
 #endif
-                if (off + words + gen_words <= Frame::kArenaWords) {
+                if (off + words <= Frame::kArenaWords) {
 #if defined(__CUDA_ARCH__)
                     job = atomicAdd(&f.n_tjobs, 1);
 #else
@@ -1701,7 +1734,7 @@ struct Raster {
 #else
             slot = f.n_gen++;
 #endif
-            if ((slot + 1) * (int)(sizeof(Blit) / 4) + f.tile_top > Frame::kArenaWords) {
+            if (slot >= Frame::kGenSmem && f.gen_spill == nullptr) {
                 c.h->err |= ERR_TILE_ARENA;
                 continue;
             }
@@ -1818,14 +1851,20 @@ struct Raster {
 
     // What a thread keeps for the four pixel columns of its quad while it walks down the rows.
     struct QuadCtx {
-        uint32_t ci[4];                    // colinfo
+        uint32_t ci[4];                    // colinfo (flags)
+        uint32_t cbase[4];                 // cell column * ny
+        uint32_t tile_dx[4], tile_tw[4];   // column of the pixel inside its cell's tile, row stride of that tile
         uint32_t bg_sx[4];                 // single-image background: source column per pixel column (BG_NONE outside)
         bool bg_one;
     };
     static PG_HD void quad_begin(const Frame &f, int px0, QuadCtx &q) {
         q.bg_one = f.pad == 1;
         for (int k = 0; k < 4; k++) {
-            q.ci[k] = G::DRAWS_GRID ? f.colinfo[px0 + k] : 0u;
+            const uint32_t ci = G::DRAWS_GRID ? f.colinfo[px0 + k] : 0u;
+            q.ci[k] = ci;
+            q.cbase[k] = ci & CI_BASE_MASK;
+            q.tile_dx[k] = (ci >> CI_D_SHIFT) & 31u;
+            q.tile_tw[k] = (ci >> CI_TW_SHIFT) & 31u;
             q.bg_sx[k] = q.bg_one ? bg_column(f, px0 + k) : 0u;
         }
     }
@@ -1834,31 +1873,38 @@ struct Raster {
 
     // Four horizontally adjacent pixels of row py -> fb. The inline part covers the common pixel —
     // at most one cell and that one from a pre-scaled tile: tile texel first, the background (or
-    // what is already in fb) only when the texel is not opaque.
+    // what is already in fb) only when the texel is not opaque. Pixels of overlap strips are left to
+    // gather_strips (GATHER_ALL stores a placeholder there, GATHER_CELLS leaves fb alone).
     template <int MODE>
     static PG_HD void gather_quad(const Frame &f, const QuadCtx &q, int px0, int py, const uint32_t *atlas, uint32_t *fb) {
         const uint32_t rowinfo = (G::DRAWS_GRID && MODE != GATHER_BG) ? f.rowinfo[py] : 0u;
         const uint32_t bgrow = q.bg_one ? f.bgrow[py] : BG_NONE;
+        const uint32_t rbase = rowinfo & CI_BASE_MASK, dy = (rowinfo >> CI_D_SHIFT) & 31u;
         uint32_t *dst = fb + py * RES_W + px0;
+        uint32_t s[4];
+        uint32_t slow = 0, strip = 0;
         for (int k = 0; k < 4; k++) {
-            const uint32_t ci = q.ci[k];
-            uint32_t s = 0;
-            bool slow = false;
-            if (G::DRAWS_GRID && MODE != GATHER_BG && (ci & rowinfo & CI_VALID)) {
-                if ((ci | rowinfo) & CI_MULTI) {
-                    continue;  // a strip where cells overlap: left to gather_strips
-                } else {
-                    const uint32_t code = f.cellmap[(ci & CI_BASE_MASK) + (rowinfo & CI_BASE_MASK)];
+            s[k] = 0;
+            if (G::DRAWS_GRID && MODE != GATHER_BG) {
+                const uint32_t both = q.ci[k] & rowinfo;
+                if (both & CI_FAST) {  // one cell column and one cell row cover the pixel
+                    const uint32_t code = f.cellmap[q.cbase[k] + rbase];
                     if (code & CELL_GENERAL)
-                        slow = true;
+                        slow |= 1u << k;
                     else if (code)
-                        s = f.arena[(int)code - 1 + (int)((rowinfo >> CI_D_SHIFT) & 31u) * (int)((ci >> CI_TW_SHIFT) & 31u) + (int)((ci >> CI_D_SHIFT) & 31u)];
+                        s[k] = f.arena[code - 1 + dy * q.tile_tw[k] + q.tile_dx[k]];
+                } else if (both & CI_VALID) {
+                    strip |= 1u << k;
                 }
             }
-            if (s >= 0xff000000u && !slow) {
-                dst[k] = s;
+        }
+        uint32_t c[4];
+        for (int k = 0; k < 4; k++) {
+            c[k] = s[k];
+            if ((strip >> k) & 1u)
                 continue;
-            }
+            if (s[k] >= 0xff000000u && !((slow >> k) & 1u))
+                continue;
             uint32_t under;
             if (MODE == GATHER_CELLS)
                 under = dst[k];
@@ -1866,10 +1912,21 @@ struct Raster {
                 under = bg_single(bgrow, q.bg_sx[k], atlas);
             else
                 under = bg_generic(f, px0 + k, py, atlas);
-            if (slow)
-                dst[k] = cells_generic(f, px0 + k, py, atlas, under);
+            if ((slow >> k) & 1u)
+                c[k] = cells_generic(f, px0 + k, py, atlas, under);
             else
-                dst[k] = s != 0 ? s + pg_byte_mul(under, (~s) >> 24) : under;
+                c[k] = s[k] != 0 ? s[k] + pg_byte_mul(under, (~s[k]) >> 24) : under;
+        }
+        if (MODE == GATHER_CELLS) {
+            for (int k = 0; k < 4; k++)
+                if (!((strip >> k) & 1u))
+                    dst[k] = c[k];
+        } else {
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(c[0], c[1], c[2], c[3]);
+#else
+            for (int k = 0; k < 4; k++) dst[k] = c[k];
+#endif
         }
     }
 

@@ -676,11 +676,12 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     fill_tensortypes(v);
 
     // ---- state arrays
-    int ent_cap = 0, grid_cap = 0, scratch_words = 0, rot_records = 0, blit_records = 0, setup_bytes = 0;
+    int ent_cap = 0, grid_cap = 0, scratch_words = 0, rot_records = 0, blit_records = 0, setup_bytes = 0, cell_records = 0;
     for (auto g : v->games) {
         rot_records = std::max(rot_records, g->rot_records);
         blit_records = std::max(blit_records, g->blit_records);
         setup_bytes = std::max(setup_bytes, g->setup_bytes);
+        cell_records = std::max(cell_records, g->cell_records);
         ent_cap = std::max(ent_cap, g->ent_cap);
         grid_cap = std::max(grid_cap, g->grid_cap);
         scratch_words = std::max(scratch_words, g->scratch_words);
@@ -700,6 +701,8 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
     p.rot_scratch = rot_records > 0 ? dev_alloc<RotBlit>(N * (size_t)rot_records) : nullptr;
     p.blit_stride = blit_records;
     p.blit_list = dev_alloc<Blit>(N * (size_t)blit_records);
+    p.cell_spill_stride = cell_records;
+    p.cell_spill = dev_alloc<Blit>(N * (size_t)cell_records);
     p.frame_setup_stride = (setup_bytes + 15) & ~15;
     p.frame_setup = dev_alloc<unsigned char>(N * (size_t)p.frame_setup_stride);
     p.atlas = v->d_atlas;
@@ -914,6 +917,7 @@ void libenv_close(libenv_env *handle) {
         dev_free(p.rot_scratch);
     dev_free(p.blit_list);
     dev_free(p.frame_setup);
+    dev_free(p.cell_spill);
     dev_free(v->d_atlas);
     dev_free(v->d_tile_texels);
     dev_free(v->d_tile_index);
