@@ -122,7 +122,10 @@ struct RenderTune {
 #else
     // 227 KiB usable per SM, 1 KiB reserved per resident CTA
     static constexpr int kFit = (int)((227 * 1024) / (kFrameBytes + 1024 + 16));
-    static constexpr int kMinBlocks = kFit >= 8 ? 8 : (kFit >= 1 ? kFit : 1);
+    // measured (profiles/r02_ab_render_ctas.txt): the games that draw grid cells run best at 7 CTAs (72
+    // registers: at 64 the gather loop spills), the entity-only games at 8
+    static constexpr int kWant = G::DRAWS_GRID ? 7 : 8;
+    static constexpr int kMinBlocks = kFit >= kWant ? kWant : (kFit >= 1 ? kFit : 1);
 #endif
 };
 
