@@ -10,7 +10,7 @@ struct CaveFlyerGame : Defaults<CaveFlyerGame>, DrawDefaults<CaveFlyerGame> {
     static constexpr int ENT_CAP = 192;
     static constexpr int GRID_CAP = 60 * 60;
     static constexpr int SCRATCH_WORDS = 18 * GRID_CAP;
-    static constexpr int MAX_VISIBLE_ENTS = 64;
+    static constexpr int MAX_VISIBLE_ENTS = 192;
     static constexpr int MAX_ROT_BLITS = 32;
     static constexpr int MAX_VIEW_CELLS = 20;  // visibility 16 centred
     static constexpr const char *NAME = "caveflyer";

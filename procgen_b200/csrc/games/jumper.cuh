@@ -19,7 +19,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
     static constexpr int MAZE_WORDS = 3200;  // MazeGen::words_needed(15) = 3081
     static constexpr int ROOM_WORDS = 12 * GRID_CAP;
     static constexpr int SCRATCH_WORDS = MAZE_WORDS + ROOM_WORDS + 5 * GRID_CAP;
-    static constexpr int MAX_VISIBLE_ENTS = 128;
+    static constexpr int MAX_VISIBLE_ENTS = 320;
     static constexpr int MAX_ROT_BLITS = 3;    // no sprite rotates; the slots hold the compass disc, its needle and the double-jump shadow
     static constexpr int MAX_VIEW_CELLS = 20;  // visibility 16: int(c-9)..int(c+9)
     static constexpr const char *NAME = "jumper";

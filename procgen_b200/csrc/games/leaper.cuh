@@ -19,7 +19,7 @@ struct LeaperGame : Defaults<LeaperGame>, DrawDefaults<LeaperGame> {
     static constexpr int ENT_CAP = 160;
     static constexpr int GRID_CAP = 20 * 20;
     static constexpr int SCRATCH_WORDS = 0;
-    static constexpr int MAX_VISIBLE_ENTS = 128;
+    static constexpr int MAX_VISIBLE_ENTS = 160;
     static constexpr int MAX_ROT_BLITS = 4;
     static constexpr int MAX_VIEW_CELLS = 20;
     static constexpr const char *NAME = "leaper";
