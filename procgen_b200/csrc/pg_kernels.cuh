@@ -71,6 +71,7 @@ PG_HD Ctx make_ctx(const KParams &p, int env) {
     c.obst_hi = -1;
     c.rot_scratch_raw = (p.rot_scratch && p.rot_stride > 0) ? (void *)(p.rot_scratch + (size_t)env * p.rot_stride) : nullptr;
     c.blit_list = p.blit_list ? p.blit_list + (size_t)env * p.blit_stride : nullptr;
+    c.cell_spill = p.cell_spill ? p.cell_spill + (size_t)env * p.cell_spill_stride : nullptr;
     ctx_refresh(c);
     return c;
 }
@@ -185,30 +186,24 @@ PG_HD void env_setup_frame(const KParams &p, int env, Setup &f, int lane, int nl
     }
     if (lane == 0)
         R::frame_append_overlays(f);
-}
-
-template <class G, class Frame>
-PG_HD void env_render_begin(const KParams &p, int env, Frame &f, int tid, int nthreads) {
-    Raster<G, Frame>::render_begin(f, p.cell_spill ? p.cell_spill + (size_t)env * p.cell_spill_stride : nullptr, tid, nthreads);
-}
-
-template <class G, class Frame>
-PG_HD void env_render_build(const KParams &p, int env, Frame &f, int tid, int nthreads, int ent_group) {
-    Ctx c = make_ctx(p, env);
-    Raster<G, Frame>::frame_build(c, f, tid, nthreads, ent_group);
-}
-
-// tile registration results -> arena space + staging jobs
-template <class G, class Frame>
-PG_HD void env_render_jobs(const KParams &p, int env, Frame &f, int tid, int nthreads) {
-    Ctx c = make_ctx(p, env);
-    Raster<G, Frame>::frame_tile_alloc(c, f, p.tiles, tid, nthreads);
-}
-
-template <class G, class Frame>
-PG_HD void env_render_masks(const KParams &p, int env, Frame &f, int tid, int nthreads) {
-    Ctx c = make_ctx(p, env);
-    Raster<G, Frame>::frame_cells_finish(c, f, tid, nthreads);
+    // cells: pixel -> cell lookups, classification, the tiles they need and where those will sit in the
+    // render CTA's arena
+    if (G::DRAWS_GRID) {
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        R::frame_build(c, f, lane, nlanes, 0);
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        R::frame_tile_alloc(c, f, p.tiles, lane, nlanes);
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        R::frame_cells_finish(c, f, lane, nlanes);
+    } else {
+        R::frame_build(c, f, lane, nlanes, 0);  // background row offsets only
+    }
 }
 
 // Host debug harness twin of the bulk copies that stage the frame's tiles

@@ -166,10 +166,9 @@ __device__ __forceinline__ void pg_bulk_store_and_wait(void *dst_gmem, const voi
 }
 
 // One CTA renders one env's frame:
-//   begin                  stage what the setup kernel prepared (spans, background, counts) with one bulk copy
-//   build / jobs           the cell map and the list of pre-scaled tiles the frame needs
-//   stage                  warp 0 arms the mbarrier and queues one bulk copy per tile (global table -> shared)
-//   cells                  meanwhile: the cells learn where their tiles are
+//   stage                  warp 0 arms the mbarrier and queues the bulk copies: what the setup kernel prepared
+//                          (spans, background, counts, cell map, lookups) and one per pre-scaled tile (global
+//                          table -> shared arena)
 //   compose                warp w owns rows y = w (mod 4): gather (cells over background; a lane = 4 pixel
 //                          columns x 8 rows), then paint the entity blits in draw order, lanes sharing each blit
 //   pack + store           RGB32 -> RGB888 in place, one bulk copy of the 12 KiB frame to the observation buffer
@@ -193,38 +192,28 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
 #define PG_RENDER_PHASE(id) do { } while (0)
 #endif
     using Shared = typename FrameFor<G>::shared;
-    if (tid == 0) {
-        // what the setup kernel prepared for this env: one bulk copy into the head of the frame
+    using Setup = typename FrameFor<G>::setup;
+    const Setup *gs = reinterpret_cast<const Setup *>(p.frame_setup + (size_t)env * p.frame_setup_stride);
+    if (tid == 0)
         pg_mbar_init(&f.mbar, 1);
-        pg_mbar_arrive_expect_tx(&f.mbar, (unsigned)sizeof(Shared));
-        pg_bulk_load(static_cast<Shared *>(&f), p.frame_setup + (size_t)env * p.frame_setup_stride, (unsigned)sizeof(Shared), &f.mbar);
-    }
-    env_render_begin<G, Frame>(p, env, f, tid, kRenderThreads);
-    __syncthreads();   // mbarrier initialised + counters cleared
-    pg_mbar_wait(&f.mbar, 0);
-    PG_RENDER_PHASE(0);
-    env_render_build<G, Frame>(p, env, f, tid, kRenderThreads, 32);
     __syncthreads();
-    PG_RENDER_PHASE(1);
-    env_render_jobs<G, Frame>(p, env, f, tid, kRenderThreads);
-    __syncthreads();
-    PG_RENDER_PHASE(2);
-    if (G::DRAWS_GRID && tid < 32) {
-        const int nj = f.n_tjobs < MAX_TILE_JOBS ? f.n_tjobs : MAX_TILE_JOBS;
+    if (tid < 32) {
+        // Everything the setup kernel prepared for this env — one bulk copy into the head of the frame —
+        // and the pre-scaled tiles its cells need, one bulk copy each, all counted on one mbarrier phase.
+        const int nj = G::DRAWS_GRID ? (gs->n_tjobs < MAX_TILE_JOBS ? gs->n_tjobs : MAX_TILE_JOBS) : 0;
+        unsigned words = 0;
+        for (int j = tid; j < nj; j += 32) words += gs->tjob_words[j];
+        for (int d = 16; d > 0; d >>= 1) words += __shfl_xor_sync(0xffffffffu, words, d);
         if (tid == 0) {
-            unsigned bytes = 0;
-            for (int j = 0; j < nj; j++) bytes += 4u * f.tjob_words[j];
-            pg_mbar_arrive_expect_tx(&f.mbar, bytes);
+            pg_mbar_arrive_expect_tx(&f.mbar, (unsigned)sizeof(Shared) + 4u * words);
+            pg_bulk_load(static_cast<Shared *>(&f), static_cast<const Shared *>(gs), (unsigned)sizeof(Shared), &f.mbar);
         }
         __syncwarp();
-        for (int j = tid; j < nj; j += 32) pg_bulk_load(f.arena + f.tjob_dst[j], p.tiles.texels + f.tjob_src[j], 4u * f.tjob_words[j], &f.mbar);
+        for (int j = tid; j < nj; j += 32)
+            pg_bulk_load(f.arena + gs->tjob_dst[j], p.tiles.texels + gs->tjob_src[j], 4u * gs->tjob_words[j], &f.mbar);
     }
-    env_render_masks<G, Frame>(p, env, f, tid, kRenderThreads);
-    __syncthreads();
-    PG_RENDER_PHASE(3);
-    if (G::DRAWS_GRID)
-        pg_mbar_wait(&f.mbar, 1);
-    PG_RENDER_PHASE(4);
+    pg_mbar_wait(&f.mbar, 0);
+    PG_RENDER_PHASE(0);
     // warp w owns rows y = w (mod warps): gather and paint need no block barrier in between
     env_render_compose<G, Frame>(p, f, tid >> 5, kRenderThreads >> 5, tid & 31, 32);
     __syncthreads();
@@ -306,11 +295,7 @@ void render_env_serial(const KParams &p, int env, Frame &f) {
     Setup &s = *reinterpret_cast<Setup *>(p.frame_setup + (size_t)env * p.frame_setup_stride);
     env_setup_frame<G, Setup>(p, env, s, 0, 1);
     static_cast<Shared &>(f) = static_cast<const Shared &>(s);
-    env_render_begin<G, Frame>(p, env, f, 0, 1);
-    env_render_build<G, Frame>(p, env, f, 0, 1, 1);
-    env_render_jobs<G, Frame>(p, env, f, 0, 1);
     env_stage_tiles_serial<Frame>(p, f);
-    env_render_masks<G, Frame>(p, env, f, 0, 1);
     for (int w = 0; w < 4; w++) env_render_compose<G, Frame>(p, f, w, 4, 0, 1);  // the device's row ownership, one lane per owner
     uint32_t *out = reinterpret_cast<uint32_t *>(p.rgb + (size_t)env * (RES_W * RES_H * 3));
     for (int g = 0; g < RES_W * RES_H / 4; g++) Raster<G, Frame>::pack_quad(f.fb + 4 * g, out + 3 * g);

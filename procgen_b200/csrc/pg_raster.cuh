@@ -98,12 +98,13 @@ constexpr uint32_t CI_MULTI = 1u << 21;          // more than one cell column / 
 constexpr uint32_t CI_FAST = 1u << 22;           // exactly one does
 
 // One frame's working set, in three parts:
-//   FrameSharedT  what the setup kernel (one warp per env: camera, cell spans, background and entity
-//                 blits — everything that is O(entities + cell columns) and heavy on fp64) hands to the
-//                 render kernel. Lives in global memory; the render CTA stages it into its shared
-//                 memory with one bulk copy.
+//   FrameSharedT  what the setup kernel (one warp per env) hands to the render kernel: camera, cell
+//                 spans, background, blit counts, the classified cell map with its pixel -> cell
+//                 lookups, and the list of pre-scaled tiles to stage — everything that is O(entities
+//                 + cells) and heavy on fp64 or control flow. Lives in global memory; the render
+//                 CTA stages it into its shared memory with one bulk copy.
 //   FrameSetupT   + the setup kernel's own scratch (global, per env)
-//   FrameT        + the render kernel's scratch (shared memory): frame buffer, tile arena, cell map
+//   FrameT        + the render kernel's scratch (shared memory): frame buffer, tile arena
 template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
 struct alignas(16) FrameSharedT {
     static constexpr int kMaxCells1D = MAX_CELLS_1D;
@@ -111,6 +112,8 @@ struct alignas(16) FrameSharedT {
     // `ents` = VISIBLE entity blits (after culling) in draw order, then the overlay blits (drawn last)
     static constexpr int kMaxEntBlits = MAX_ENT_BLITS;
     static constexpr int kMaxList = MAX_ENT_BLITS + MAX_OVERLAY_BLITS;
+    // shared-memory words the render CTA keeps for staged tiles; tiles that do not fit turn their cells into general blits
+    static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? (MAX_CELLS_1D * MAX_CELLS_1D * 8 < 1280 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 1280) : 4;
     Camera cam;
     int32_t low_x, low_y, nx, ny;   // visible grid window: cells [low_x, low_x+nx) x [low_y, low_y+ny)
     int32_t n_bg, n_ent, n_ent_below, n_overlay;  // n_ent_below = entities with render_z == -1
@@ -118,9 +121,14 @@ struct alignas(16) FrameSharedT {
     int32_t pad;                    // 1: the background is one opaque un-mirrored image (it may cover only part of the device)
     int32_t tile_w0, tile_h0;       // smaller of the two snapped cell sizes of this frame
     int32_t n_rot;
-    int32_t spare[3];
+    int32_t n_gen;                  // general cell blits in use (gen_spill)
+    int32_t tile_top;               // arena words used by tiles
+    int32_t n_tjobs;
     RotBlit *rot;                   // this env's rotated-sprite / span records (global)
     Blit *ents;                     // this env's blit list (global): the painter reads it sequentially
+    Blit *gen_spill;                // this env's general cell blits (global): solid-colour cells, clipped walks that differ, un-snapped targets
+    int32_t n_strip_cols;           // pixel columns where two cell columns overlap
+    int32_t spare;
     // geometry shared by all cells of a column / row (the cell rect is separable)
     double cell_w;                  // QRectF.width == height
     double spare_d;
@@ -130,7 +138,19 @@ struct alignas(16) FrameSharedT {
     uint8_t row_p1[MAX_CELLS_1D], row_p2[MAX_CELLS_1D];
     uint8_t col_tw[MAX_CELLS_1D], row_th[MAX_CELLS_1D];  // snapped size if the column / row can use tiles, else 0
     uint8_t col_k0[MAX_CELLS_1D], row_k0[MAX_CELLS_1D];  // pixels the device edge cuts off the near side (tile offset of the first visible one)
-    Blit bg[MAX_BG_BLITS];
+    uint8_t strip_cols[RES_W];
+    uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
+    uint8_t row_lo[RES_H], row_hi[RES_H];
+    alignas(4) uint32_t colinfo[RES_W];
+    uint32_t rowinfo[RES_H];                  // CI_* words
+    uint32_t bgrow[RES_H];                    // pad == 1: atlas offset of the background row sampled by pixel row py, BG_NONE outside the image
+    uint32_t tjob_src[MAX_TILE_JOBS];         // tile copies to stage: texel offset in the table,
+    uint16_t tjob_dst[MAX_TILE_JOBS], tjob_words[MAX_TILE_JOBS];  // arena word offset, words
+    uint16_t cellmap[MAX_CELLS_1D * MAX_CELLS_1D];  // [ci * ny + cj], x outer / y inner = draw order
+    alignas(16) Blit bg[MAX_BG_BLITS];
+
+    PG_HD Blit *gen_blit(int k) { return gen_spill + k; }
+    PG_HD const Blit *gen_blit(int k) const { return gen_spill + k; }
 };
 
 template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
@@ -142,6 +162,7 @@ struct alignas(16) FrameSetupT : FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_R
     int32_t n_jobs;
     int32_t job_ei[kMaxTileJobs], job_pos[kMaxTileJobs], job_n[kMaxTileJobs], job_j0[kMaxTileJobs];
     Blit overlay[MAX_OVERLAY_BLITS];
+    alignas(4) uint16_t tilekey[MAX_CELLS_1D > 1 ? CELL_KEYS : 4];  // per (type, size variant): 0 unused | 1 wanted | 2 + arena texel offset | 0xffff unavailable
 };
 
 template <int MAX_CELLS_1D, int MAX_ENT_BLITS, int MAX_ROT_BLITS>
@@ -150,31 +171,8 @@ struct alignas(16) FrameT : FrameSharedT<MAX_CELLS_1D, MAX_ENT_BLITS, MAX_ROT_BL
     // the frame as 0xFFRRGGBB pixels while it is composed; packed to RGB888 in place (its first
     // 12 KiB) and written out with one bulk store
     alignas(16) uint32_t fb[RES_W * RES_H];
-    // staged tiles (texels); tiles that do not fit turn their cells into general blits
-    static constexpr int kArenaWords = MAX_CELLS_1D > 1 ? (MAX_CELLS_1D * MAX_CELLS_1D * 8 < 1280 ? MAX_CELLS_1D * MAX_CELLS_1D * 8 : 1280) : 4;
-    alignas(16) uint32_t arena[kArenaWords];
-    // general cell blits: the first few here, the rest in the env's global spill slice (frames of
-    // solid-colour cells, un-snapped targets, monochrome mode: every cell is one)
-    static constexpr int kGenSmem = MAX_CELLS_1D > 1 ? 32 : 1;
-    Blit gen_smem[kGenSmem];
-    Blit *gen_spill;
-    alignas(8) unsigned long long mbar;   // staging barrier: phase 0 the shared part, phase 1 the tiles
-    int32_t n_gen;                  // general cell blits in use
-    int32_t tile_top;               // arena words used by tiles
-    int32_t n_tjobs;
-    int32_t n_strip_cols;                                // pixel columns where two cell columns overlap
-    uint8_t strip_cols[RES_W];
-    uint8_t col_lo[RES_W], col_hi[RES_W];   // window-relative cell columns covering pixel column
-    uint8_t row_lo[RES_H], row_hi[RES_H];
-    uint32_t colinfo[RES_W], rowinfo[RES_H];  // CI_* words
-    uint32_t bgrow[RES_H];                    // pad == 1: atlas offset of the background row sampled by pixel row py, BG_NONE outside the image
-    uint16_t cellmap[MAX_CELLS_1D * MAX_CELLS_1D];  // [ci * ny + cj], x outer / y inner = draw order
-    alignas(4) uint16_t tilekey[MAX_CELLS_1D > 1 ? CELL_KEYS : 4];  // per (type, size variant): 0 unused | 1 wanted | 2 + arena texel offset | 0xffff unavailable
-    uint32_t tjob_src[MAX_TILE_JOBS];         // tile copies to stage: texel offset in the table,
-    uint16_t tjob_dst[MAX_TILE_JOBS], tjob_words[MAX_TILE_JOBS];  // arena word offset, words
-
-    PG_HD Blit *gen_blit(int k) { return k < kGenSmem ? gen_smem + k : gen_spill + (k - kGenSmem); }
-    PG_HD const Blit *gen_blit(int k) const { return k < kGenSmem ? gen_smem + k : gen_spill + (k - kGenSmem); }
+    alignas(16) uint32_t arena[Shared::kArenaWords];   // staged tiles (texels)
+    alignas(8) unsigned long long mbar;                // staging barrier (shared part + tiles)
 };
 
 // ---- rule S: un-rotated scaled image (qt_scale_image_32bit)
@@ -1205,10 +1203,15 @@ struct Raster {
             f.n_ent_below = 0;
             f.n_rot = 0;
             f.n_jobs = 0;
+            f.n_gen = 0;
+            f.tile_top = 0;
+            f.n_tjobs = 0;
+            f.n_strip_cols = 0;
             f.tile_w0 = f.tile_h0 = w0;
             f.cell_w = cw[2];
             f.rot = reinterpret_cast<RotBlit *>(c.rot_scratch_raw);
             f.ents = c.blit_list;
+            f.gen_spill = c.cell_spill;
             if (overflow)
                 h.err |= ERR_BLIT_OVERFLOW;
             if (h.options.use_backgrounds)
@@ -1239,6 +1242,10 @@ struct Raster {
             }
             G::make_overlay_blits(c, f);  // game overlays are appended after the velocity squares
         }
+        if (G::DRAWS_GRID) {
+            uint32_t *keys = reinterpret_cast<uint32_t *>(f.tilekey);
+            for (int i = tid; i < CELL_KEYS / 2; i += nthreads) keys[i] = 0;
+        }
         // columns by lanes 0.., rows by lanes from the top end
         for (int i = tid; i < nx; i += nthreads) {
             double r[4];
@@ -1256,21 +1263,6 @@ struct Raster {
             uint8_t ts;
             span_of(r[1], r[3], snap, RES_H, f.row_p1[j], f.row_p2[j], ts, f.row_k0[j]);
             f.row_th[j] = (ts == w0 || ts == w0 + 1) ? ts : 0;
-        }
-    }
-
-    // ---- render kernel, phase B: its own counters and the tile registration table
-    static PG_HD void render_begin(Frame &f, Blit *gen_spill, int tid, int nthreads) {
-        if (tid == 0) {
-            f.gen_spill = gen_spill;
-            f.n_gen = 0;
-            f.tile_top = 0;
-            f.n_tjobs = 0;
-            f.n_strip_cols = 0;
-        }
-        if (G::DRAWS_GRID) {
-            uint32_t *keys = reinterpret_cast<uint32_t *>(f.tilekey);
-            for (int i = tid; i < CELL_KEYS / 2; i += nthreads) keys[i] = 0;
         }
     }
 
@@ -1587,7 +1579,7 @@ struct Raster {
         return true;
     }
 
-    // ---- render kernel, phase C: pixel -> cell lookups and the first pass over the visible cells
+    // ---- setup kernel, step 3: pixel -> cell lookups and the first pass over the visible cells
     static PG_HD void frame_build(Ctx &c, Frame &f, int tid, int nthreads, int /*unused*/) {
         const int wtid = tid, wn = nthreads;
         if (f.pad == 1) {
@@ -1661,10 +1653,6 @@ struct Raster {
             make_sprite_blit(c, f, b, r, 0, false, type, theme, 1.0f);
             if (b.kind == BLIT_NONE)
                 continue;
-            if (slot >= Frame::kGenSmem && f.gen_spill == nullptr) {
-                c.h->err |= ERR_TILE_ARENA;
-                continue;
-            }
             *f.gen_blit(slot) = b;
             f.cellmap[k] = (uint16_t)(CELL_GENERAL | slot);
         }
@@ -1734,10 +1722,6 @@ struct Raster {
 #else
             slot = f.n_gen++;
 #endif
-            if (slot >= Frame::kGenSmem && f.gen_spill == nullptr) {
-                c.h->err |= ERR_TILE_ARENA;
-                continue;
-            }
             const int ci = k / f.ny, cj = k - ci * f.ny;
             const int type = key >> 2;
             Blit b;

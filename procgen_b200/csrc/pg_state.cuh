@@ -165,6 +165,7 @@ struct Ctx {
     int32_t scratch_cap;  // in int32 words
     void *rot_scratch_raw; // per-env slice for rotated-sprite / span records (setup + render kernels)
     struct Blit *blit_list; // per-env blit list the setup kernel fills and the render kernel paints
+    struct Blit *cell_spill; // per-env general cell blits (setup kernel writes, render kernel reads)
     // register-resident copies of header scalars the physics loop reads constantly; refreshed by
     // ctx_refresh() whenever a game changes them (world size is chosen per episode)
     int32_t mw, mh, oob;
