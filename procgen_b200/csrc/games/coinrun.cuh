@@ -16,10 +16,10 @@ struct CoinRunState {
 
 struct CoinRun : Defaults<CoinRun>, DrawDefaults<CoinRun> {
     using E = Engine<CoinRun>;
-    static constexpr int ENT_CAP = 256;
+    static constexpr int ENT_CAP = 512;  // observed > 256 live entities (trails of many enemies) in 65 536-env rollouts
     static constexpr int GRID_CAP = 64 * 64;
     static constexpr int SCRATCH_WORDS = 0;
-    static constexpr int MAX_VISIBLE_ENTS = 256;  // = ENT_CAP: the blit list lives in global memory, no reason to be tight
+    static constexpr int MAX_VISIBLE_ENTS = 512;  // = ENT_CAP: the blit list lives in global memory, no reason to be tight
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 17;  // visibility 13: int(c-7.5)..int(c+7.5) -> <= 16 cells
     static constexpr const char *NAME = "coinrun";

@@ -1614,6 +1614,19 @@ struct Raster {
         // adjusted rects, no snapping) becomes a general blit right away.
         const int ncells = f.nx * f.ny;
         const bool mono = c.h->options.use_monochrome_assets != 0;
+#if defined(__CUDA_ARCH__)
+        // the window's grid rows are ny short segments in ny different cache lines: touch them all at
+        // once so the classification loop below runs on cache hits
+        for (int j = wtid; j < f.ny; j += wn) {
+            const int gy = f.low_y + j, gx = f.low_x < 0 ? 0 : f.low_x;
+            if (gy >= 0 && gy < c.mh && gx < c.mw) {
+                const int16_t *row = c.grid + gy * c.mw + gx;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+                if (f.nx > 32 || ((reinterpret_cast<uintptr_t>(row) & 127) + 2 * f.nx > 128))
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(row + f.nx - 1 < c.grid + c.mh * c.mw ? row + f.nx - 1 : row));
+            }
+        }
+#endif
         for (int k = wtid; k < ncells; k += wn) {
             int ci = k / f.ny, cj = k - ci * f.ny;
             f.cellmap[k] = 0;
@@ -1622,10 +1635,14 @@ struct Raster {
             int type = E::get_obj(c, f.low_x + ci, f.low_y + cj);
             if (type == INVALID_OBJ)
                 continue;
+            // most of a level is empty: draw_image returns before drawing anything when the image type is
+            // negative, and draw_grid_obj when it is SPACE (basic-abstract-game.cpp:880-882, 916)
+            const int img_type = G::image_for_type(c, type);
+            if (img_type < 0 || img_type == SPACE)
+                continue;
             const int theme = G::theme_for_grid_obj(c, type);
             const int tw = f.col_tw[ci], th = f.row_th[cj];
             if (tw && th && !mono && type >= 0 && type < CELL_KEY_TYPES && theme >= 0 && theme < MAX_IMAGE_THEMES) {
-                const int img_type = G::image_for_type(c, type);
                 double adj[4];
                 bool ok = img_type >= 0 && img_type < USE_ASSET_THRESHOLD && !G::get_adjusted_image_rect(c, img_type, adj);
                 if (ok && (f.col_k0[ci] | f.row_k0[cj])) {
