@@ -423,6 +423,7 @@ def run_ours(args):
     pairs = max(1, ktimes["launch_pairs"])
     render_ms_avg = ktimes["render_ms"] / pairs
     logic_ms_avg = ktimes["logic_ms"] / pairs
+    setup_ms_avg = ktimes["setup_ms"] / pairs
     envs_per_launch = ktimes["env_steps"] / pairs
     algo_bytes_per_launch = ALGO_BYTES_PER_ENV_STEP * envs_per_launch
     achieved = algo_bytes_per_launch / (render_ms_avg / 1000.0) / 1e9 if render_ms_avg > 0 else 0.0
@@ -461,7 +462,7 @@ def run_ours(args):
                      "kernel": f"render_kernel<{args.game}>",
                      "kernel_ms_avg": render_ms_avg, "launches_timed": ktimes["launch_pairs"], "envs_per_launch": envs_per_launch,
                      "algorithmic_bytes_per_launch": algo_bytes_per_launch,
-                     "logic_kernel_ms_avg": logic_ms_avg, "step_ms_avg": step_ms,
+                     "logic_kernel_ms_avg": logic_ms_avg, "setup_kernel_ms_avg": setup_ms_avg, "step_ms_avg": step_ms,
                      "how": "CUDA events around each launch, launches serialised on one stream (separate pass of %d steps, "
                             "steady state)" % Kr,
                      "whole_step_achieved": ALGO_BYTES_PER_ENV_STEP * n / (step_ms / 1000.0) / 1e9},

@@ -218,10 +218,11 @@ LIBENV_API int pgb200_frame_info(const char *game, int *frame_bytes, int *ctas_p
 LIBENV_API int64_t pgb200_kernel_launches(libenv_env *handle);
 
 /* Per-kernel device timing for measurement (bench.py roofline): between begin and end every
- * (logic_kernel, render_kernel) launch pair is bracketed by CUDA events on the stream it runs on.
- * end() synchronises and writes out[0] = sum of logic-kernel ms, out[1] = sum of render-kernel ms,
- * out[2] = number of launch pairs timed, out[3] = env-steps those launches processed; returns the
- * number of pairs. At most max_launch_pairs pairs are timed (further launches run untimed). */
+ * (logic_kernel, setup_kernel, render_kernel) launch triple is bracketed by CUDA events on the stream it
+ * runs on. end() synchronises and writes out[0] = sum of logic-kernel ms, out[1] = sum of render-kernel
+ * ms, out[2] = number of launch triples timed, out[3] = env-steps those launches processed, out[4] =
+ * sum of setup-kernel ms (out must hold 5 doubles); returns the number of triples. At most
+ * max_launch_pairs triples are timed (further launches run untimed). */
 LIBENV_API int pgb200_kernel_timing_begin(libenv_env *handle, int max_launch_pairs);
 /* Measurement knob: chunks > 0 forces that many env chunks per game and step (0 = the default
  * policy); serialize != 0 keeps every launch on the handle's stream, back to back, so a kernel's

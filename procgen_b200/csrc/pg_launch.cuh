@@ -98,8 +98,11 @@ __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kern
 // same code, which is what the instruction cache wants; the render kernel that follows — one CTA
 // per env — is left with the O(pixels + cells) work and picks the result up with one bulk copy.
 constexpr int kSetupThreads = 128;
+#ifndef PG_SETUP_MIN_BLOCKS
+#define PG_SETUP_MIN_BLOCKS 5
+#endif
 template <class G>
-__global__ void __launch_bounds__(kSetupThreads) setup_kernel(KParams p) {
+__global__ void __launch_bounds__(kSetupThreads, PG_SETUP_MIN_BLOCKS) setup_kernel(KParams p) {
     using Setup = typename FrameFor<G>::setup;
     const int i = (int)blockIdx.x * (kSetupThreads / 32) + (int)(threadIdx.x >> 5);
     if (i >= p.env_count)
@@ -309,7 +312,7 @@ struct LaunchCtx {
     unsigned int *ticket;     // work counter of this launch slot (one per in-flight logic kernel)
     int max_logic_blocks;     // SM count x resident CTAs per SM
     int render_smem_floor;    // dynamic shared memory requested per render CTA is at least this (co-residency knob)
-    cudaEvent_t *tev;         // optional: 3 events (before logic, between, after render) for kernel timing
+    cudaEvent_t *tev;         // optional: 4 events (before logic, after it, after setup, after render) for kernel timing
 #endif
     int64_t *launch_counter;
 };
@@ -360,9 +363,11 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
     setup_kernel<G><<<(p.env_count + kSetupThreads / 32 - 1) / (kSetupThreads / 32), kSetupThreads, 0, lc.stream>>>(p);
-    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
+    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
+    if (lc.tev)
+        CUDA_CHECK(cudaEventRecord(lc.tev[3], lc.stream));
     CUDA_CHECK(cudaGetLastError());
     (*lc.launch_counter) += 3;
 #else

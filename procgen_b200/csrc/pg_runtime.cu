@@ -341,9 +341,9 @@ struct VecEnv {
                     }
                 }
                 lc.ticket = d_tickets + (k % kMaxTickets);
-                if (timing && tev_used + 3 <= tev_pool.size()) {
+                if (timing && tev_used + 4 <= tev_pool.size()) {
                     lc.tev = &tev_pool[tev_used];
-                    tev_used += 3;
+                    tev_used += 4;
                     tev_envs.push_back(p.env_count);
                 }
 #endif
@@ -1252,7 +1252,7 @@ int pgb200_kernel_timing_begin(libenv_env *handle, int max_launch_pairs) {
     VecEnv *v = (VecEnv *)handle;
     v->set_device();
     v->sync();
-    while ((int)v->tev_pool.size() < 3 * max_launch_pairs) {
+    while ((int)v->tev_pool.size() < 4 * max_launch_pairs) {
         cudaEvent_t e;
         CUDA_CHECK(cudaEventCreate(&e));
         v->tev_pool.push_back(e);
@@ -1272,20 +1272,23 @@ int pgb200_kernel_timing_end(libenv_env *handle, double *out) {
     v->set_device();
     v->sync();
     v->timing = false;
-    double logic_ms = 0, render_ms = 0, envs = 0;
-    const int pairs = (int)(v->tev_used / 3);
+    double logic_ms = 0, setup_ms = 0, render_ms = 0, envs = 0;
+    const int pairs = (int)(v->tev_used / 4);
     for (int i = 0; i < pairs; i++) {
-        float a = 0, b = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&a, v->tev_pool[3 * i], v->tev_pool[3 * i + 1]));
-        CUDA_CHECK(cudaEventElapsedTime(&b, v->tev_pool[3 * i + 1], v->tev_pool[3 * i + 2]));
+        float a = 0, b = 0, c2 = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&a, v->tev_pool[4 * i], v->tev_pool[4 * i + 1]));
+        CUDA_CHECK(cudaEventElapsedTime(&b, v->tev_pool[4 * i + 1], v->tev_pool[4 * i + 2]));
+        CUDA_CHECK(cudaEventElapsedTime(&c2, v->tev_pool[4 * i + 2], v->tev_pool[4 * i + 3]));
         logic_ms += a;
-        render_ms += b;
+        setup_ms += b;
+        render_ms += c2;
         envs += v->tev_envs[i];
     }
     out[0] = logic_ms;
     out[1] = render_ms;
     out[2] = pairs;
     out[3] = envs;
+    out[4] = setup_ms;
     v->tev_used = 0;
     v->tev_envs.clear();
     return pairs;

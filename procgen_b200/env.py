@@ -348,9 +348,9 @@ class BaseProcgenEnv:
     def kernel_timing_end(self) -> dict:
         import ctypes as C
 
-        out = (C.c_double * 4)()
+        out = (C.c_double * 5)()
         pairs = int(self._lib.pgb200_kernel_timing_end(self._h, out))
-        return {"logic_ms": out[0], "render_ms": out[1], "launch_pairs": pairs, "env_steps": out[3]}
+        return {"logic_ms": out[0], "render_ms": out[1], "setup_ms": out[4], "launch_pairs": pairs, "env_steps": out[3]}
 
     def enable_peer_gather(self, dst: int = 0) -> bool:
         """Turn gather_observations() into peer writes: allocate the gathered array as torch symmetric
