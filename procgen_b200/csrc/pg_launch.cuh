@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kLogicThreads, PG_LOGIC_MIN_BLOCKS) logic_kern
 // per env — is left with the O(pixels + cells) work and picks the result up with one bulk copy.
 constexpr int kSetupThreads = 128;
 #ifndef PG_SETUP_MIN_BLOCKS
-#define PG_SETUP_MIN_BLOCKS 5
+#define PG_SETUP_MIN_BLOCKS 8   // measured (profiles/r02_ab_setup_kernel_occupancy.txt): 64 registers x 32 warps/SM beats 96 x 20
 #endif
 template <class G>
 __global__ void __launch_bounds__(kSetupThreads, PG_SETUP_MIN_BLOCKS) setup_kernel(KParams p) {
