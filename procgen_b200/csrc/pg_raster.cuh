@@ -980,8 +980,9 @@ struct Raster {
     }
 
     // draw_image (basic-abstract-game.cpp:877-913) for the un-rotated, un-tiled case
-    static PG_HD_NOINLINE void make_sprite_blit(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
+    static PG_HD_NOINLINE void make_sprite_blit(Ctx &cref, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
                                                 int defer_ei = -1) {
+        Ctx c = cref;  // private copy: see Engine::sub_step
         blit_clear(b);
         int img_type = G::image_for_type(c, base_type);
         if (img_type < 0)
@@ -1089,7 +1090,8 @@ struct Raster {
     }
 
     // draw_image's inner part for an already-resolved image type and already-adjusted rect
-    static PG_HD_NOINLINE void make_sprite_blit_noadjust(Ctx &c, Frame &f, Blit &b, double *rect, bool is_reflected, int img_type, int theme, float alpha) {
+    static PG_HD_NOINLINE void make_sprite_blit_noadjust(Ctx &cref, Frame &f, Blit &b, double *rect, bool is_reflected, int img_type, int theme, float alpha) {
+        Ctx c = cref;
         blit_clear(b);
         if (theme < 0 || theme >= MAX_IMAGE_THEMES) {
             c.h->err |= ERR_FASSERT;
