@@ -59,7 +59,7 @@ static inline void pg_fatal(const char *fmt, ...) {
 #define PG_STEP_CHUNKS 8
 #endif
 #ifndef PG_AUX_STREAMS
-#define PG_AUX_STREAMS 8
+#define PG_AUX_STREAMS 16   // one per game of the 16-game list: the slow games (level generation) must not queue behind each other
 #endif
 constexpr int kLogicThreads = 32 * PG_LOGIC_WARPS;  // one warp = one env; few warps per CTA so a finished
 constexpr int kLogicEnvsPerBlock = PG_LOGIC_WARPS;  // env frees its slot without waiting on many siblings

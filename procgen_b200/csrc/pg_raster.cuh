@@ -134,8 +134,12 @@ struct alignas(16) FrameSharedT {
     double spare_d;
     double col_x[MAX_CELLS_1D];     // QRectF.x of column i
     double row_y[MAX_CELLS_1D];     // QRectF.y of row j
-    uint8_t col_p1[MAX_CELLS_1D], col_p2[MAX_CELLS_1D];  // device pixel span [p1,p2) of column i
-    uint8_t row_p1[MAX_CELLS_1D], row_p2[MAX_CELLS_1D];
+    // device pixel span [p1,p2) of column i; padded to whole words with 255 (cell_lookup compares 4 at a time)
+    static constexpr int kSpanBytes = (MAX_CELLS_1D + 3) & ~3;
+    alignas(4) uint8_t col_p1[kSpanBytes];
+    alignas(4) uint8_t col_p2[kSpanBytes];
+    alignas(4) uint8_t row_p1[kSpanBytes];
+    alignas(4) uint8_t row_p2[kSpanBytes];
     uint8_t col_tw[MAX_CELLS_1D], row_th[MAX_CELLS_1D];  // snapped size if the column / row can use tiles, else 0
     uint8_t col_k0[MAX_CELLS_1D], row_k0[MAX_CELLS_1D];  // pixels the device edge cuts off the near side (tile offset of the first visible one)
     uint8_t strip_cols[RES_W];
@@ -1266,51 +1270,48 @@ struct Raster {
             span_of(r[1], r[3], snap, RES_H, f.row_p1[j], f.row_p2[j], ts, f.row_k0[j]);
             f.row_th[j] = (ts == w0 || ts == w0 + 1) ? ts : 0;
         }
+        for (int i = nx + tid; i < Frame::kSpanBytes; i += nthreads) f.col_p1[i] = f.col_p2[i] = 255;
+        for (int j = ny + tid; j < Frame::kSpanBytes; j += nthreads) f.row_p1[j] = f.row_p2[j] = 255;
     }
 
     // cell columns (rows) covering pixel column (row) p -> lo / hi and the packed CI_* word
+    // Spans are monotonic in the cell index (columns left to right; rows bottom-up, i.e. decreasing), so the
+    // cells covering pixel p are a contiguous index range that two counts give: how many spans start at or
+    // before p, how many end at or before p. Four spans per compare (byte-wise SIMD on the device).
     static PG_HD uint32_t cell_lookup(const uint8_t *p1, const uint8_t *p2, const uint8_t *tsize, const uint8_t *k0, int n, int base_mul, int px, uint8_t &lo,
                                       uint8_t &hi) {
-        int l = 255, hgh = 0;
-        // spans are monotonic: only the columns around the proportional estimate can cover px
-        // (cell spans differ from the ideal grid by less than a pixel; +-3 also covers 1-pixel cells)
-        int first = 0, last = n - 1;
-        if (n > 8) {
-            const bool reversed = p1[n - 1] < p1[0];  // cell rows run bottom-up: pixel spans decrease with the index
-            const int span0 = reversed ? p1[n - 1] : p1[0], span1 = reversed ? p2[0] : p2[n - 1];
-            int est = span1 > span0 ? ((px - span0) * n) / (span1 - span0) : 0;
-            if (reversed)
-                est = n - 1 - est;
-            first = est - 3 < 0 ? 0 : est - 3;
-            last = est + 3 > n - 1 ? n - 1 : est + 3;
+        int started = 0, ended = 0;
+#if defined(__CUDA_ARCH__)
+        const uint32_t pv = (uint32_t)px * 0x01010101u;
+        const uint32_t *w1 = reinterpret_cast<const uint32_t *>(p1), *w2 = reinterpret_cast<const uint32_t *>(p2);
+        for (int w = 0; w < Frame::kSpanBytes / 4; w++) {
+            started += __popc(__vcmpleu4(w1[w], pv));   // padding bytes are 255: never counted
+            ended += __popc(__vcmpleu4(w2[w], pv));
         }
-        for (int i = first; i <= last; i++) {
-            if (px >= p1[i] && px < p2[i]) {
-                if (l == 255) {
-                    l = i;
-                    hgh = i;
-                } else {
-                    if (i < l) l = i;
-                    if (i > hgh) hgh = i;
-                }
-            }
+        started >>= 3;
+        ended >>= 3;
+#else
+        for (int i = 0; i < n; i++) {
+            started += p1[i] <= px;
+            ended += p2[i] <= px;
         }
-        if (n > 8 && (l == 255 || (l == first && first > 0) || (hgh == last && last < n - 1))) {
-            // nothing found, or a hit on the rim of the window (a neighbour outside it could overlap): scan all
-            l = 255;
-            hgh = 0;
-            for (int i = 0; i < n; i++) {
-                if (px >= p1[i] && px < p2[i]) {
-                    if (l == 255)
-                        l = i;
-                    hgh = i;
-                }
-            }
+#endif
+        const bool reversed = n > 1 && p1[n - 1] < p1[0];
+        int l, hgh;
+        if (!reversed) {
+            l = ended;
+            hgh = started - 1;
+        } else {
+            l = n - started;
+            hgh = n - ended - 1;
+        }
+        if (l > hgh) {
+            lo = 255;
+            hi = 0;
+            return 0;
         }
         lo = (uint8_t)l;
         hi = (uint8_t)hgh;
-        if (l == 255)
-            return 0;
         uint32_t w = (uint32_t)(hgh * base_mul) | CI_VALID | ((uint32_t)((px - p1[hgh] + k0[hgh]) & 31) << CI_D_SHIFT) | ((uint32_t)tsize[hgh] << CI_TW_SHIFT);
         w |= l != hgh ? CI_MULTI : CI_FAST;
         return w;
@@ -1629,8 +1630,15 @@ struct Raster {
             }
         }
 #endif
+        int ci = f.ny > 0 ? wtid / f.ny : 0, cj = wtid - ci * f.ny;  // (ci, cj) of cell k, advanced without dividing
         for (int k = wtid; k < ncells; k += wn) {
-            int ci = k / f.ny, cj = k - ci * f.ny;
+            if (k != wtid) {
+                cj += wn;
+                while (cj >= f.ny) {
+                    cj -= f.ny;
+                    ci++;
+                }
+            }
             f.cellmap[k] = 0;
             if (f.col_p1[ci] >= f.col_p2[ci] || f.row_p1[cj] >= f.row_p2[cj])
                 continue;  // entirely off screen
