@@ -1900,10 +1900,19 @@ struct Raster {
                 const uint32_t both = q.ci[k] & rowinfo;
                 if (both & CI_FAST) {  // one cell column and one cell row cover the pixel
                     const uint32_t code = f.cellmap[q.cbase[k] + rbase];
-                    if (code & CELL_GENERAL)
-                        slow |= 1u << k;
-                    else if (code)
+                    if (code & CELL_GENERAL) {
+                        // solid-colour cells (chaser's orbs, monochrome mode) are a box test; other kinds take the long way
+                        const Blit &gb = *f.gen_blit((int)(code & 0x7fffu));
+                        if (gb.kind == BLIT_SOLID) {
+                            const uint32_t box = *reinterpret_cast<const uint32_t *>(&gb);
+                            const uint32_t ddx = (uint32_t)(px0 + k) - (box & 0xffu), ddy = (uint32_t)py - ((box >> 8) & 0xffu);
+                            s[k] = (ddx < ((box >> 16) & 0xffu) && ddy < (box >> 24)) ? gb.src : 0u;
+                        } else {
+                            slow |= 1u << k;
+                        }
+                    } else if (code) {
                         s[k] = f.arena[code - 1 + dy * q.tile_tw[k] + q.tile_dx[k]];
+                    }
                 } else if (both & CI_VALID) {
                     strip |= 1u << k;
                 }
