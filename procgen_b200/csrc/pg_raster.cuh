@@ -1983,77 +1983,41 @@ struct Raster {
         }
     }
 
-    // rows of a blit's box that belong to the row set {row_first, row_first + row_step, ...}
-    static PG_HD void blit_rows(uint32_t box, int row_first, int row_step, int &x1, int &y1, int &w, int &r0, int &n) {
-        x1 = (int)(box & 0xffu);
-        y1 = (int)((box >> 8) & 0xffu);
-        w = (int)((box >> 16) & 0xffu);
-        const int h = (int)(box >> 24);
-        r0 = (row_first - y1) % row_step;  // first row of the box that is ours
-        if (r0 < 0)
-            r0 += row_step;
-        const int nrows = (w != 0 && r0 < h) ? (h - 1 - r0) / row_step + 1 : 0;
-        n = nrows * w;
-    }
-    // source value of blit b at pixel idx of our rows of its box
-    static PG_HD uint32_t blit_pixel(const Frame &f, const Blit &b, int x1, int y1, int w, int r0, int row_step, int idx, const uint32_t *atlas, int &at) {
-        const int r = idx / w, dx = idx - r * w, dy = r0 + r * row_step;
-        at = (y1 + dy) * RES_W + x1 + dx;
-        if (b.kind == BLIT_IMAGE) {
-            uint32_t sx = (b.basex + (uint32_t)b.ix * (uint32_t)dx) >> 16;
-            const uint32_t sy = (b.srcy + (uint32_t)b.iy * (uint32_t)dy) >> 16;
-            if (b.mirror)
-                sx = b.sw - 1 - sx;
-            return layer_of(atlas[b.src + sy * b.sw + sx], b.opacity);
-        }
-        return blit_texel(b, x1 + dx, y1 + dy, atlas, f.rot);
-    }
-
     // Paint blits [lo, hi) of the entity list, in list order, onto the rows row_first, row_first +
     // row_step, ... of fb. The `nlanes` threads that share those rows split every blit's pixels.
-    // Painting is a chain of dependent latencies (blit record -> texel -> blend), so blits are taken
-    // four at a time: the records and texels of all four are fetched first (independent loads, in
-    // flight together), then blended in list order. A blit with more pixels in our rows than lanes
-    // takes the plain loop at its place in the order.
     static PG_HD void paint_blits(const Frame &f, uint32_t *fb, int lo, int hi, int row_first, int row_step, int lane, int nlanes, const uint32_t *atlas) {
-        constexpr int B = 4;
-        for (int i0 = lo; i0 < hi; i0 += B) {
-            uint32_t sv[B];
-            int at[B];
-            bool big[B];
-            for (int b = 0; b < B; b++) {
-                sv[b] = 0;
-                at[b] = 0;
-                big[b] = false;
-                const int i = i0 + b;
-                if (i >= hi)
-                    continue;
-                const Blit &bl = f.ents[i];
-                int x1, y1, w, r0, n;
-                blit_rows(*reinterpret_cast<const uint32_t *>(&bl), row_first, row_step, x1, y1, w, r0, n);
-                if (n > nlanes)
-                    big[b] = true;
-                else if (lane < n)
-                    sv[b] = blit_pixel(f, bl, x1, y1, w, r0, row_step, lane, atlas, at[b]);
-            }
-            for (int b = 0; b < B; b++) {
-                if (big[b]) {
-                    const Blit &bl = f.ents[i0 + b];
-                    int x1, y1, w, r0, n;
-                    blit_rows(*reinterpret_cast<const uint32_t *>(&bl), row_first, row_step, x1, y1, w, r0, n);
-                    for (int idx = lane; idx < n; idx += nlanes) {
-                        int a;
-                        const uint32_t s0 = blit_pixel(f, bl, x1, y1, w, r0, row_step, idx, atlas, a);
-                        if (s0 != 0)
-                            fb[a] = layer_over(fb[a], s0);
-                    }
-                } else if (sv[b] != 0) {
-                    fb[at[b]] = layer_over(fb[at[b]], sv[b]);
+        for (int i = lo; i < hi; i++) {
+            const Blit &b = f.ents[i];
+            const uint32_t box = *reinterpret_cast<const uint32_t *>(&b);  // x1 | y1<<8 | w<<16 | h<<24
+            const int x1 = (int)(box & 0xffu), y1 = (int)((box >> 8) & 0xffu), w = (int)((box >> 16) & 0xffu), h = (int)(box >> 24);
+            if (w == 0)
+                continue;
+            int r0 = (row_first - y1) % row_step;  // first row of the box that is ours
+            if (r0 < 0)
+                r0 += row_step;
+            const int nrows = r0 < h ? (h - 1 - r0) / row_step + 1 : 0;
+            const int n = nrows * w;
+            const bool plain = b.kind == BLIT_IMAGE;
+            for (int idx = lane; idx < n; idx += nlanes) {
+                const int r = idx / w, dx = idx - r * w, dy = r0 + r * row_step;
+                uint32_t s;
+                if (plain) {
+                    uint32_t sx = (b.basex + (uint32_t)b.ix * (uint32_t)dx) >> 16;
+                    const uint32_t sy = (b.srcy + (uint32_t)b.iy * (uint32_t)dy) >> 16;
+                    if (b.mirror)
+                        sx = b.sw - 1 - sx;
+                    s = layer_of(atlas[b.src + sy * b.sw + sx], b.opacity);
+                } else {
+                    s = blit_texel(b, x1 + dx, y1 + dy, atlas, f.rot);
                 }
-#if defined(__CUDA_ARCH__)
-                __syncwarp();  // the next blit may overlap this one
-#endif
+                if (s != 0) {
+                    uint32_t *px = fb + (y1 + dy) * RES_W + x1 + dx;
+                    *px = layer_over(*px, s);
+                }
             }
+#if defined(__CUDA_ARCH__)
+            __syncwarp();  // the next blit may overlap this one
+#endif
         }
     }
 
