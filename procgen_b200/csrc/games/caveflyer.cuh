@@ -13,6 +13,7 @@ struct CaveFlyerGame : Defaults<CaveFlyerGame>, DrawDefaults<CaveFlyerGame> {
     static constexpr int MAX_VISIBLE_ENTS = 192;
     static constexpr int MAX_ROT_BLITS = 32;
     static constexpr int MAX_VIEW_CELLS = 20;  // visibility 16 centred
+    static constexpr int FULL_VIEW_CELLS = 60;  // center_agent = false: the whole world (basic-abstract-game.cpp:819-838)
     static constexpr const char *NAME = "caveflyer";
     // superset of the types is_blocked (:49-55) and will_reflect (:80) accept
     static PG_HD bool may_be_obstacle(Ctx &c, int t) { return t == WALL_OBJ || t == c.oob || t == CAVEWALL; }

@@ -17,6 +17,7 @@ struct Climber : Defaults<Climber>, DrawDefaults<Climber> {
     static constexpr int MAX_VISIBLE_ENTS = 64;
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 24;  // visibility = main_width (<= 20): int(c-11)..int(c+11)
+    static constexpr int FULL_VIEW_CELLS = 64;  // center_agent = false: the whole world (basic-abstract-game.cpp:819-838)
     static constexpr const char *NAME = "climber";
 
     // climber.cpp:9-26

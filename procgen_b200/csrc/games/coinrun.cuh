@@ -22,6 +22,7 @@ struct CoinRun : Defaults<CoinRun>, DrawDefaults<CoinRun> {
     static constexpr int MAX_VISIBLE_ENTS = 512;  // = ENT_CAP: the blit list lives in global memory, no reason to be tight
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 17;  // visibility 13: int(c-7.5)..int(c+7.5) -> <= 16 cells
+    static constexpr int FULL_VIEW_CELLS = 64;  // center_agent = false: the whole world (basic-abstract-game.cpp:819-838)
     static constexpr const char *NAME = "coinrun";
 
     // coinrun.cpp:11-34

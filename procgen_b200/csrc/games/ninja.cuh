@@ -17,6 +17,7 @@ struct Ninja : Defaults<Ninja>, DrawDefaults<Ninja> {
     static constexpr int MAX_VISIBLE_ENTS = 64;
     static constexpr int MAX_ROT_BLITS = 0;
     static constexpr int MAX_VIEW_CELLS = 20;  // visibility 16: int(c-9)..int(c+9)
+    static constexpr int FULL_VIEW_CELLS = 64;  // center_agent = false: the whole world (basic-abstract-game.cpp:819-838)
     static constexpr const char *NAME = "ninja";
 
     // ninja.cpp:9-21

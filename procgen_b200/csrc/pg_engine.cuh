@@ -943,6 +943,9 @@ struct Defaults {
     // false = the game never writes its grid (all SPACE) and always draws the whole world
     // (center_agent forced off): the frame then carries no cell blits at all
     static constexpr bool DRAWS_GRID = true;
+    // > 0: the game honours center_agent = false by drawing its whole world (basic-abstract-game.cpp:
+    // 819-838); cells per side of that view (its largest world dimension)
+    static constexpr int FULL_VIEW_CELLS = 0;
     // true = rotated sprites are scan-converted in a separate all-thread phase of the render kernel
     // instead of by the thread that owns the entity. Pays off where a frame mixes sprite kinds (a
     // warp then serialises a different long code path per lane); measured per game, B200:

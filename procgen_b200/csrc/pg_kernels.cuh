@@ -235,10 +235,12 @@ PG_HD void tile_table_fill(const SpriteDesc *sprites, const uint32_t *index, uin
 }
 
 // Frame sizing per game: visible window (cells per side) and entity capacity.
-template <class G>
+// VIEW = cells per side of the largest visible grid window: G::MAX_VIEW_CELLS for the game's usual view,
+// G::FULL_VIEW_CELLS for the whole-world view the scrolling games draw with center_agent = false
+template <class G, int VIEW = G::MAX_VIEW_CELLS>
 struct FrameFor {
-    using type = FrameT<(G::DRAWS_GRID ? G::MAX_VIEW_CELLS : 1), G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
-    using setup = FrameSetupT<(G::DRAWS_GRID ? G::MAX_VIEW_CELLS : 1), G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
+    using type = FrameT<(G::DRAWS_GRID ? VIEW : 1), G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
+    using setup = FrameSetupT<(G::DRAWS_GRID ? VIEW : 1), G::MAX_VISIBLE_ENTS, G::MAX_ROT_BLITS>;
     using shared = typename type::Shared;
 };
 

@@ -101,9 +101,9 @@ constexpr int kSetupThreads = 128;
 #ifndef PG_SETUP_MIN_BLOCKS
 #define PG_SETUP_MIN_BLOCKS 8   // measured (profiles/r02_ab_setup_kernel_occupancy.txt): 64 registers x 32 warps/SM beats 96 x 20
 #endif
-template <class G>
+template <class G, int VIEW>
 __global__ void __launch_bounds__(kSetupThreads, PG_SETUP_MIN_BLOCKS) setup_kernel(KParams p) {
-    using Setup = typename FrameFor<G>::setup;
+    using Setup = typename FrameFor<G, VIEW>::setup;
     const int i = (int)blockIdx.x * (kSetupThreads / 32) + (int)(threadIdx.x >> 5);
     if (i >= p.env_count)
         return;
@@ -117,9 +117,9 @@ __global__ void __launch_bounds__(kSetupThreads, PG_SETUP_MIN_BLOCKS) setup_kern
 #endif
 // Resident CTAs per SM the render kernel is compiled for: as many as the frame (shared memory)
 // allows; the register cap follows (65536 / (128 * CTAs)).
-template <class G>
+template <class G, int VIEW>
 struct RenderTune {
-    static constexpr size_t kFrameBytes = sizeof(typename FrameFor<G>::type);
+    static constexpr size_t kFrameBytes = sizeof(typename FrameFor<G, VIEW>::type);
 #ifdef PG_RENDER_MIN_BLOCKS
     static constexpr int kMinBlocks = PG_RENDER_MIN_BLOCKS;
 #else
@@ -175,9 +175,9 @@ __device__ __forceinline__ void pg_bulk_store_and_wait(void *dst_gmem, const voi
 //   compose                warp w owns rows y = w (mod 4): gather (cells over background; a lane = 4 pixel
 //                          columns x 8 rows), then paint the entity blits in draw order, lanes sharing each blit
 //   pack + store           RGB32 -> RGB888 in place, one bulk copy of the 12 KiB frame to the observation buffer
-template <class G>
-__global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) render_kernel(KParams p) {
-    using Frame = typename FrameFor<G>::type;
+template <class G, int VIEW>
+__global__ void __launch_bounds__(kRenderThreads, RenderTune<G, VIEW>::kMinBlocks) render_kernel(KParams p) {
+    using Frame = typename FrameFor<G, VIEW>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Frame &f = *reinterpret_cast<Frame *>(smem_raw);
     const int env = p.env_first + (int)blockIdx.x * p.env_step;
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(kRenderThreads, RenderTune<G>::kMinBlocks) ren
 #else
 #define PG_RENDER_PHASE(id) do { } while (0)
 #endif
-    using Shared = typename FrameFor<G>::shared;
-    using Setup = typename FrameFor<G>::setup;
+    using Shared = typename FrameFor<G, VIEW>::shared;
+    using Setup = typename FrameFor<G, VIEW>::setup;
     const Setup *gs = reinterpret_cast<const Setup *>(p.frame_setup + (size_t)env * p.frame_setup_stride);
     if (tid == 0)
         pg_mbar_init(&f.mbar, 1);
@@ -291,10 +291,10 @@ __global__ void camera_kernel(KParams p) {
 #endif
 
 // the setup + render kernels' phases as plain loops (host debug harness; also documents the phase order)
-template <class G, class Frame>
+template <class G, int VIEW, class Frame>
 void render_env_serial(const KParams &p, int env, Frame &f) {
-    using Setup = typename FrameFor<G>::setup;
-    using Shared = typename FrameFor<G>::shared;
+    using Setup = typename FrameFor<G, VIEW>::setup;
+    using Shared = typename FrameFor<G, VIEW>::shared;
     Setup &s = *reinterpret_cast<Setup *>(p.frame_setup + (size_t)env * p.frame_setup_stride);
     env_setup_frame<G, Setup>(p, env, s, 0, 1);
     static_cast<Shared &>(f) = static_cast<const Shared &>(s);
@@ -320,9 +320,9 @@ struct LaunchCtx {
 #ifndef PG_HOSTSIM
 // Dynamic shared memory of one render CTA (frame, or the co-residency floor) with the kernel's
 // opt-in limit raised to it once.
-template <class G>
+template <class G, int VIEW>
 int prepare_render_smem(const LaunchCtx &lc) {
-    using Frame = typename FrameFor<G>::type;
+    using Frame = typename FrameFor<G, VIEW>::type;
     const int bytes = (int)sizeof(Frame) > lc.render_smem_floor ? (int)sizeof(Frame) : lc.render_smem_floor;
     // the attribute is per device: remember what each device of this process was given
     static int attr_set[64] = {};
@@ -330,16 +330,16 @@ int prepare_render_smem(const LaunchCtx &lc) {
     CUDA_CHECK(cudaGetDevice(&dev));
     int &have = attr_set[dev & 63];
     if (have < bytes) {
-        CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        CUDA_CHECK(cudaFuncSetAttribute(render_kernel<G, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         have = bytes;
     }
     return bytes;
 }
 #endif
 
-template <class G, bool INIT>
+template <class G, bool INIT, int VIEW>
 void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
-    using Frame = typename FrameFor<G>::type;
+    using Frame = typename FrameFor<G, VIEW>::type;
     if (p.env_count <= 0)
         return;
 #ifndef PG_HOSTSIM
@@ -347,7 +347,7 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     // render CTAs per SM. At 8 CTAs x 128 threads x 64 registers the render kernel owns the whole
     // register file of an SM and no logic-kernel block of another env chunk can run beside it;
     // capping its residency trades a little render speed for real overlap of the two kernels.
-    const int render_smem = prepare_render_smem<G>(lc);
+    const int render_smem = prepare_render_smem<G, VIEW>(lc);
     int logic_blocks = (p.env_count + kLogicEnvsPerBlock - 1) / kLogicEnvsPerBlock;
     if (logic_blocks > lc.max_logic_blocks)
         logic_blocks = lc.max_logic_blocks;
@@ -362,10 +362,10 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
     }
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[1], lc.stream));
-    setup_kernel<G><<<(p.env_count + kSetupThreads / 32 - 1) / (kSetupThreads / 32), kSetupThreads, 0, lc.stream>>>(p);
+    setup_kernel<G, VIEW><<<(p.env_count + kSetupThreads / 32 - 1) / (kSetupThreads / 32), kSetupThreads, 0, lc.stream>>>(p);
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[2], lc.stream));
-    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
+    render_kernel<G, VIEW><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
     if (lc.tev)
         CUDA_CHECK(cudaEventRecord(lc.tev[3], lc.stream));
     CUDA_CHECK(cudaGetLastError());
@@ -378,22 +378,22 @@ void launch_env_kernel(const KParams &p, const LaunchCtx &lc) {
             env_init_logic<G, Frame>(p, env);
         else
             env_step_logic<G, Frame>(p, env);
-        render_env_serial<G, Frame>(p, env, *f);
+        render_env_serial<G, VIEW, Frame>(p, env, *f);
     }
     (*lc.launch_counter) += 3;
 #endif
 }
 
-template <class G>
+template <class G, int VIEW>
 void launch_observe_only(const KParams &p, const LaunchCtx &lc) {
-    using Frame = typename FrameFor<G>::type;
+    using Frame = typename FrameFor<G, VIEW>::type;
     if (p.env_count <= 0)
         return;
 #ifndef PG_HOSTSIM
-    const int render_smem = prepare_render_smem<G>(lc);
+    const int render_smem = prepare_render_smem<G, VIEW>(lc);
     camera_kernel<G><<<p.env_count, 32, 0, lc.stream>>>(p);
-    setup_kernel<G><<<(p.env_count + kSetupThreads / 32 - 1) / (kSetupThreads / 32), kSetupThreads, 0, lc.stream>>>(p);
-    render_kernel<G><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
+    setup_kernel<G, VIEW><<<(p.env_count + kSetupThreads / 32 - 1) / (kSetupThreads / 32), kSetupThreads, 0, lc.stream>>>(p);
+    render_kernel<G, VIEW><<<p.env_count, kRenderThreads, render_smem, lc.stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
 #else
     static thread_local Frame *f = new Frame;
@@ -402,7 +402,7 @@ void launch_observe_only(const KParams &p, const LaunchCtx &lc) {
         Ctx c = make_ctx(p, env);
         Raster<G, Frame>::prepare_camera(c);
         write_step_outputs(p, env, *c.h);
-        render_env_serial<G, Frame>(p, env, *f);
+        render_env_serial<G, VIEW, Frame>(p, env, *f);
     }
 #endif
     (*lc.launch_counter) += 2;
@@ -414,27 +414,46 @@ struct GameVTable {
     int ent_cap, grid_cap, scratch_words;
     int rot_records;  // rotated-sprite / span records per env (global)
     int blit_records; // blit list capacity per env (global)
-    int setup_bytes;  // sizeof(FrameSetupT) of the game
-    int cell_records; // cells of the largest visible window (spill capacity for general cell blits)
-    int frame_bytes;  // shared memory of one render CTA
-    int render_ctas_per_sm;  // residency the render kernel is compiled for
-    void (*init)(const KParams &, const LaunchCtx &);
-    void (*step)(const KParams &, const LaunchCtx &);
-    void (*observe_only)(const KParams &, const LaunchCtx &);
+    // [0] = the game's usual view, [1] = the whole-world view of center_agent = false (step[1] null: the game has none)
+    int setup_bytes[2];   // sizeof(FrameSetupT)
+    int cell_records[2];  // cells of the largest visible window (capacity for general cell blits)
+    int frame_bytes[2];   // shared memory of one render CTA
+    int render_ctas_per_sm[2];  // residency the render kernel is compiled for
+    void (*init[2])(const KParams &, const LaunchCtx &);
+    void (*step[2])(const KParams &, const LaunchCtx &);
+    void (*observe_only[2])(const KParams &, const LaunchCtx &);
 };
+
+template <class G, int VIEW>
+void fill_view(GameVTable &vt, int slot) {
+    using F = FrameFor<G, VIEW>;
+    vt.setup_bytes[slot] = (int)sizeof(typename F::setup);
+    vt.cell_records[slot] = F::type::kMaxCells1D * F::type::kMaxCells1D;
+    vt.frame_bytes[slot] = (int)sizeof(typename F::type);
+#ifndef PG_HOSTSIM
+    vt.render_ctas_per_sm[slot] = RenderTune<G, VIEW>::kMinBlocks;
+#else
+    vt.render_ctas_per_sm[slot] = 0;
+#endif
+    vt.init[slot] = &launch_env_kernel<G, true, VIEW>;
+    vt.step[slot] = &launch_env_kernel<G, false, VIEW>;
+    vt.observe_only[slot] = &launch_observe_only<G, VIEW>;
+}
 
 template <class G>
 GameVTable make_vtable(int id) {
-    return GameVTable{G::NAME, id, G::ENT_CAP, G::GRID_CAP, G::SCRATCH_WORDS, FrameFor<G>::type::kMaxRot, FrameFor<G>::type::kMaxList, (int)sizeof(typename FrameFor<G>::setup),
-                      FrameFor<G>::type::kMaxCells1D * FrameFor<G>::type::kMaxCells1D,
-                      (int)sizeof(typename FrameFor<G>::type),
-#ifndef PG_HOSTSIM
-                      RenderTune<G>::kMinBlocks,
-#else
-                      0,
-#endif
-                      &launch_env_kernel<G, true>, &launch_env_kernel<G, false>, &launch_observe_only<G>};
+    GameVTable vt{};
+    vt.name = G::NAME;
+    vt.id = id;
+    vt.ent_cap = G::ENT_CAP;
+    vt.grid_cap = G::GRID_CAP;
+    vt.scratch_words = G::SCRATCH_WORDS;
+    vt.rot_records = FrameFor<G>::type::kMaxRot;
+    vt.blit_records = FrameFor<G>::type::kMaxList;
+    fill_view<G, G::MAX_VIEW_CELLS>(vt, 0);
+    if constexpr (G::FULL_VIEW_CELLS > G::MAX_VIEW_CELLS)
+        fill_view<G, G::FULL_VIEW_CELLS>(vt, 1);
+    return vt;
 }
-
 
 }  // namespace pg

@@ -90,12 +90,12 @@ constexpr int MAX_TILE_JOBS = 64;
 constexpr uint32_t BG_NONE = 0xffffffffu;
 
 // colinfo / rowinfo word of a pixel column / row (cells of the visible grid window)
-constexpr uint32_t CI_BASE_MASK = 0x3ffu;        // column: ci * ny; row: cj
-constexpr uint32_t CI_VALID = 1u << 10;          // some cell column / row covers the pixel
-constexpr int CI_D_SHIFT = 11;                   // 5 bits: px - col_p1 (py - row_p1)
-constexpr int CI_TW_SHIFT = 16;                  // 5 bits, column only: row stride of its tiles (0: not tile-eligible)
-constexpr uint32_t CI_MULTI = 1u << 21;          // more than one cell column / row covers the pixel
-constexpr uint32_t CI_FAST = 1u << 22;           // exactly one does
+constexpr uint32_t CI_BASE_MASK = 0xfffu;        // column: ci * ny (< 64 * 64); row: cj
+constexpr uint32_t CI_VALID = 1u << 12;          // some cell column / row covers the pixel
+constexpr int CI_D_SHIFT = 13;                   // 5 bits: px - col_p1 (py - row_p1)
+constexpr int CI_TW_SHIFT = 18;                  // 5 bits, column only: row stride of its tiles (0: not tile-eligible)
+constexpr uint32_t CI_MULTI = 1u << 23;          // more than one cell column / row covers the pixel
+constexpr uint32_t CI_FAST = 1u << 24;           // exactly one does
 
 // One frame's working set, in three parts:
 //   FrameSharedT  what the setup kernel (one warp per env) hands to the render kernel: camera, cell

@@ -212,6 +212,7 @@ struct VecEnv {
     int num_envs = 0;
     int device = -1;
     std::vector<const GameVTable *> games;  // joint games, env n <-> games[n % size] (vecgame.cpp:310)
+    std::vector<int> view;                  // per game: 0 = its usual view, 1 = the whole-world view (center_agent = false)
     std::vector<libenv_tensortype> observation_types, action_types, info_types;
     int num_actions = -1;
 
@@ -348,9 +349,9 @@ struct VecEnv {
                 }
 #endif
                 if (init)
-                    games[g]->init(p, lc);
+                    games[g]->init[view[g]](p, lc);
                 else
-                    games[g]->step(p, lc);
+                    games[g]->step[view[g]](p, lc);
 #ifndef PG_HOSTSIM
                 // libenv (host buffer) mode: start this chunk's observation DMA right behind its
                 // render kernel, on the same stream, so the copy of one chunk overlaps the kernels
@@ -545,10 +546,16 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
         const GameVTable *g = find_game(name);
         if (!g)
             pg_fatal("unknown or not yet supported env_name '%s'\n", name.c_str());
-        // These five games honour center_agent=false by drawing their whole (up to 64x64-cell)
-        // world; the render kernel's per-frame cell window is sized for the default centred view.
-        if (!center_agent && (name == "coinrun" || name == "climber" || name == "caveflyer" || name == "jumper" || name == "ninja"))
-            pg_fatal("center_agent=false is not supported for '%s' by procgen_b200 yet\n", name.c_str());
+        // Five games honour center_agent=false by drawing their whole (up to 64x64-cell) world
+        // (basic-abstract-game.cpp:819-838); four of them have a render path sized for that view. jumper's
+        // would also need Qt's generic (non-integer-rect) ellipse for its compass.
+        int view = 0;
+        if (!center_agent && (name == "coinrun" || name == "climber" || name == "caveflyer" || name == "jumper" || name == "ninja")) {
+            if (g->step[1] == nullptr)
+                pg_fatal("center_agent=false is not supported for '%s' by procgen_b200 yet\n", name.c_str());
+            view = 1;
+        }
+        v->view.push_back(view);
         // mode validity, game.cpp:56-66
         if (dist_mode == EasyMode || dist_mode == HardMode) {
         } else if (dist_mode == ExtremeMode) {
@@ -677,11 +684,12 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
 
     // ---- state arrays
     int ent_cap = 0, grid_cap = 0, scratch_words = 0, rot_records = 0, blit_records = 0, setup_bytes = 0, cell_records = 0;
-    for (auto g : v->games) {
+    for (const auto &g : v->games) {
         rot_records = std::max(rot_records, g->rot_records);
         blit_records = std::max(blit_records, g->blit_records);
-        setup_bytes = std::max(setup_bytes, g->setup_bytes);
-        cell_records = std::max(cell_records, g->cell_records);
+        const int vw = v->view[&g - &v->games[0]];
+        setup_bytes = std::max(setup_bytes, g->setup_bytes[vw]);
+        cell_records = std::max(cell_records, g->cell_records[vw]);
         ent_cap = std::max(ent_cap, g->ent_cap);
         grid_cap = std::max(grid_cap, g->grid_cap);
         scratch_words = std::max(scratch_words, g->scratch_words);
@@ -1050,7 +1058,7 @@ int pgb200_set_consumer_output(libenv_env *handle, void *buffer, int dtype, int 
         p.env_step = (int)v->games.size();
         p.env_count = v->num_envs / (int)v->games.size();
         LaunchCtx lc = v->lctx();
-        v->games[g]->observe_only(p, lc);
+        v->games[g]->observe_only[v->view[g]](p, lc);
     }
     v->sync();
     return 0;
@@ -1223,7 +1231,7 @@ void set_state(libenv_env *handle, int env_idx, char *data, int length) {
     p.env_step = 1;
     p.env_count = 1;
     LaunchCtx lc = v->lctx();
-    g->observe_only(p, lc);
+    g->observe_only[v->view[gi]](p, lc);
     v->sync();
     v->rgb_copy_enqueued = false;  // a DMA started behind the last step predates this frame: observe copies again
 }
@@ -1232,8 +1240,8 @@ int pgb200_frame_info(const char *game, int *frame_bytes, int *ctas_per_sm) {
     const GameVTable *g = find_game(game);
     if (!g)
         return -1;
-    *frame_bytes = g->frame_bytes;
-    *ctas_per_sm = g->render_ctas_per_sm;
+    *frame_bytes = g->frame_bytes[0];
+    *ctas_per_sm = g->render_ctas_per_sm[0];
     return 0;
 }
 

@@ -156,3 +156,16 @@ def test_restrict_themes_all_games(ref_lib, hostsim_lib, name):
     run_lockstep(ref, dut, 150)
     ref.close()
     dut.close()
+
+
+@pytest.mark.parametrize("name,mode", [("coinrun", "hard"), ("coinrun", "easy"), ("ninja", "hard"), ("climber", "hard"),
+                                       ("caveflyer", "hard"), ("caveflyer", "memory")])
+def test_whole_world_view_of_scrolling_games(ref_lib, hostsim_lib, name, mode):
+    """center_agent=False for the games that otherwise scroll (basic-abstract-game.cpp:819-838): the whole
+    world — up to 64 x 64 cells of about one pixel — through the full-view instantiation of the setup /
+    render kernels."""
+    ref, dut = make_pair(hostsim_lib, 8, name, distribution_mode=mode, num_levels=200, start_level=0, rand_seed=0,
+                         center_agent=False)
+    run_lockstep(ref, dut, 200)
+    ref.close()
+    dut.close()
