@@ -355,8 +355,14 @@ struct Engine {
     }
 
     // basic-abstract-game.cpp:270-372
+    // out-of-line entry for the recursion push_obj -> sub_step (crates pushing crates); the first level
+    // is inlined into basic_step_object: called 8+ times per smart entity and step, a real call there
+    // spent a third of the kernel's stack traffic on saving and restoring registers
     static PG_HD_NOINLINE bool sub_step(Ctx &cref, int oi, float _vx, float _vy, int depth) {
         Ctx c = cref;
+        return sub_step_impl(c, oi, _vx, _vy, depth);
+    }
+    static PG_HD bool sub_step_impl(Ctx &c, int oi, float _vx, float _vy, int depth) {
         Entity &obj = c.ents[oi];
         if (obj.will_erase)
             return false;
@@ -459,7 +465,8 @@ struct Engine {
                 }
             }
             if (curr_block) {
-                push_obj(cref, i, oi, is_horizontal, depth);
+                Ctx cp = c;  // only this copy's address leaves the function
+                push_obj(cp, i, oi, is_horizontal, depth);
                 moved = true;
             }
             block2 = block2 || curr_block;
@@ -494,19 +501,17 @@ struct Engine {
         }
         float vx_pct = 0;
         float vy_pct = 0;
-        // the out-of-line physics gets a COPY of the handle: only the copy's address escapes, so the
-        // caller's handle (and with it every c.h / c.ents / c.grid read of the whole step) can stay in
-        // registers; sub_step does not modify the handle
-        Ctx cs = c;
         for (int s = 0; s < num_sub_steps; s++) {
             bool block_x = false;
             bool block_y = false;
-            if (step_x_first) {
-                block_x = sub_step(cs, oi, obj.vx * pct, 0, 0);
-                block_y = sub_step(cs, oi, 0, obj.vy * pct, 0);
-            } else {
-                block_y = sub_step(cs, oi, 0, obj.vy * pct, 0);
-                block_x = sub_step(cs, oi, obj.vx * pct, 0, 0);
+            // x then y, or y then x: one inlined copy of the sub-step body, run twice
+            for (int half = 0; half < 2; half++) {
+                const bool do_x = (half == 0) == step_x_first;
+                const bool blocked = sub_step_impl(c, oi, do_x ? obj.vx * pct : 0.0f, do_x ? 0.0f : obj.vy * pct, 0);
+                if (do_x)
+                    block_x = blocked;
+                else
+                    block_y = blocked;
             }
             if (!block_x)
                 vx_pct += 1;
