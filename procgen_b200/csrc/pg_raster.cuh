@@ -185,7 +185,14 @@ PG_HD void blit_clear(Blit &b) {
     b.kind = BLIT_NONE;
 }
 
+#ifndef PG_SETUP_INLINE_BLIT
+#define PG_SETUP_INLINE_BLIT 1   // the setup kernel's per-entity blit: inlined (1) or through the out-of-line builders (0)
+#endif
+PG_HD void make_image_blit_inl(Blit &b, double tx, double ty, double tw, double th, SpriteDesc sd, bool mirror, int int_opacity, bool snap);
 PG_HD_FREE_NOINLINE void make_image_blit(Blit &b, double tx, double ty, double tw, double th, SpriteDesc sd, bool mirror, int int_opacity, bool snap) {
+    make_image_blit_inl(b, tx, ty, tw, th, sd, mirror, int_opacity, snap);
+}
+PG_HD void make_image_blit_inl(Blit &b, double tx, double ty, double tw, double th, SpriteDesc sd, bool mirror, int int_opacity, bool snap) {
     blit_clear(b);
     const int sw = sd.w, sh = sd.h;
     if (sw <= 0 || sh <= 0)
@@ -987,6 +994,17 @@ struct Raster {
     static PG_HD_NOINLINE void make_sprite_blit(Ctx &cref, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
                                                 int defer_ei = -1) {
         Ctx c = cref;  // private copy: see Engine::sub_step
+        make_sprite_blit_body<false>(c, f, b, rect, rotation, is_reflected, base_type, theme, alpha, defer_ei);
+    }
+    // the same, inlined into its caller (the per-entity site of the setup kernel: ~20 calls per frame, each
+    // of which otherwise saves and restores its registers twice, here and in make_image_blit)
+    static PG_HD void make_sprite_blit_inl(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
+                                           int defer_ei = -1) {
+        make_sprite_blit_body<true>(c, f, b, rect, rotation, is_reflected, base_type, theme, alpha, defer_ei);
+    }
+    template <bool INL>
+    static PG_HD void make_sprite_blit_body(Ctx &c, Frame &f, Blit &b, double *rect, float rotation, bool is_reflected, int base_type, int theme, float alpha,
+                                            int defer_ei) {
         blit_clear(b);
         int img_type = G::image_for_type(c, base_type);
         if (img_type < 0)
@@ -1015,7 +1033,10 @@ struct Raster {
         if (alpha != 1)
             io = (int)((double)alpha * 256);
         if (rotation == 0) {
-            make_image_blit(b, rect[0], rect[1], rect[2], rect[3], sd, is_reflected, io, f.snap != 0);
+            if (INL)
+                make_image_blit_inl(b, rect[0], rect[1], rect[2], rect[3], sd, is_reflected, io, f.snap != 0);
+            else
+                make_image_blit(b, rect[0], rect[1], rect[2], rect[3], sd, is_reflected, io, f.snap != 0);
             return;
         }
         // basic-abstract-game.cpp:901-906: translate to the rect centre, rotate, draw the centred rect
@@ -1424,7 +1445,11 @@ struct Raster {
             return nvis;
         }
 #if defined(__CUDA_ARCH__)
+#if PG_SETUP_INLINE_BLIT
+        make_sprite_blit_inl(c, f, single, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha, G::DEFER_ROTATED ? ei : -1);
+#else
         make_sprite_blit(c, f, single, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha, G::DEFER_ROTATED ? ei : -1);
+#endif
 #else
         make_sprite_blit(c, f, single, r, o.rotation, o.is_reflected != 0, o.image_type, o.image_theme, o.alpha);
 #endif
