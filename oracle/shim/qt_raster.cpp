@@ -997,15 +997,25 @@ static void ellipse_midpoint(const EllipseCtx &e) {
 //  * integer-aligned rect (jumper hard mode's compass disc at (55,1,8,8); every QRect ellipse):
 //    Qt 6.6.3 runs the midpoint algorithm above — swept against the real library, all rects.
 //  * any other rect goes through Qt's generic path code (Bezier flattening + scan conversion + a
-//    cosmetic stroke of the outline). The only such call in scope is jumper easy mode's disc,
-//    whose rect is a constant of the 64x64 contract (visibility 12, compass_dim 3): its pixel
-//    rows were captured once from Qt 6.6.3 (tests/tools/qt6_compass_mask.py) and are replayed here.
+//    cosmetic stroke of the outline). The only such calls in scope are jumper's compass disc on the
+//    three non-integer rects the 64x64 contract produces (easy mode's agent-centred view, and the
+//    whole-world views of center_agent = false in easy and hard mode): their pixel rows were
+//    captured once from Qt 6.6.3 (tests/tools/qt6_compass_mask.py) and are replayed here.
 //    Anything else is reported, never approximated.
-struct EllipseRowSpan { int y, x1, x2; };
-static const double kCompassEasyRect[4] = {46.66666793823242, 1.3333333730697632, 16.0, 16.0};
-static const EllipseRowSpan kCompassEasyRows[] = {{1, 52, 58},  {2, 50, 59},  {3, 49, 60},  {4, 48, 61},  {5, 48, 62},  {6, 47, 63},
-                                                  {7, 47, 63},  {8, 46, 63},  {9, 46, 63},  {10, 46, 63}, {11, 47, 63}, {12, 47, 63},
-                                                  {13, 47, 62}, {14, 48, 61}, {15, 49, 60}, {16, 51, 59}, {17, 53, 57}};
+struct EllipseRowSpan { int x1, x2; };
+struct CapturedDisc {
+    double x, y, w;
+    int first_row, n_rows;
+    EllipseRowSpan rows[17];
+};
+static const CapturedDisc kCompassDiscs[] = {
+    {46.66666793823242, 1.3333333730697632, 16.0, 1, 17,
+     {{52, 58}, {50, 59}, {49, 60}, {48, 61}, {48, 62}, {47, 63}, {47, 63}, {46, 63}, {46, 63}, {46, 63}, {47, 63}, {47, 63}, {47, 62}, {48, 61},
+      {49, 60}, {51, 59}, {53, 57}}},
+    {53.60000228881836, 0.800000011920929, 9.600000381469727, 0, 11,
+     {{58, 59}, {56, 61}, {55, 62}, {54, 63}, {53, 63}, {53, 64}, {53, 64}, {54, 64}, {54, 63}, {55, 62}, {57, 61}}},
+    {60.400001525878906, 0.4000000059604645, 3.200000047683716, 0, 4, {{61, 63}, {60, 64}, {60, 64}, {61, 63}}},
+};
 
 void QPainter::drawEllipse(const QRectF &rr) {
     if (nodraw())
@@ -1017,10 +1027,14 @@ void QPainter::drawEllipse(const QRectF &rr) {
     if (!integral) {
         const bool same_opaque = d->cur.pen.on && d->cur.brush.on && d->cur.pen.color.alpha() == 255 &&
                                  premul_color(d->cur.pen.color) == premul_color(d->cur.brush.color);
-        if (x == kCompassEasyRect[0] && y == kCompassEasyRect[1] && w == kCompassEasyRect[2] && h == kCompassEasyRect[3] && same_opaque &&
-            d->dev->w == 64 && d->dev->h == 64) {
-            for (const EllipseRowSpan &r : kCompassEasyRows) solid_span(d->dev, r.x1, r.x2 - r.x1, r.y, premul_color(d->cur.pen.color), io);
-            return;
+        if (same_opaque && d->dev->w == 64 && d->dev->h == 64) {
+            for (const CapturedDisc &c : kCompassDiscs) {
+                if (x == c.x && y == c.y && w == c.w && h == c.w) {
+                    for (int i = 0; i < c.n_rows; i++)
+                        solid_span(d->dev, c.rows[i].x1, c.rows[i].x2 - c.rows[i].x1, c.first_row + i, premul_color(d->cur.pen.color), io);
+                    return;
+                }
+            }
         }
         fprintf(stderr, "qt shim: drawEllipse on a non-integer rect (%.17g %.17g %.17g %.17g) is outside the restated subset\n", x, y, w, h);
         abort();

@@ -22,6 +22,7 @@ struct JumperGame : Defaults<JumperGame>, DrawDefaults<JumperGame> {
     static constexpr int MAX_VISIBLE_ENTS = 320;
     static constexpr int MAX_ROT_BLITS = 3;    // no sprite rotates; the slots hold the compass disc, its needle and the double-jump shadow
     static constexpr int MAX_VIEW_CELLS = 20;  // visibility 16: int(c-9)..int(c+9)
+    static constexpr int FULL_VIEW_CELLS = 45;  // center_agent = false: the whole world (basic-abstract-game.cpp:819-838)
     static constexpr const char *NAME = "jumper";
 
     // jumper.cpp:11-27

@@ -821,9 +821,10 @@ PG_HD void ellipse_points(RotBlit &rb, int rx, int ry, int rw, int rh, bool pen,
 }
 
 // QRasterPaintEngine::drawEllipse on a device rect (pen at most one pixel wide, same colour as the
-// brush, or no pen). Integer-aligned rects run drawEllipse_midpoint_i; the one non-aligned rect in
-// scope — jumper easy mode's compass disc, a constant of the 64x64 contract — replays the rows
-// captured from Qt 6.6.3 (tests/tools/qt6_compass_mask.py). Returns false for anything else.
+// brush, or no pen). Integer-aligned rects run drawEllipse_midpoint_i; the three non-aligned rects in
+// scope — jumper's compass disc in easy mode and in the whole-world views of center_agent = false,
+// constants of the 64x64 contract — replay the rows captured from Qt 6.6.3
+// (tests/tools/qt6_compass_mask.py). Returns false for anything else.
 template <class Frame>
 PG_HD bool make_ellipse_blit(Frame &f, Blit &b, int k, double x, double y, double w, double h, uint32_t argb_premultiplied, bool pen) {
     RotBlit *rbp = span_blit_begin(f, b, k, argb_premultiplied);
@@ -832,11 +833,25 @@ PG_HD bool make_ellipse_blit(Frame &f, Blit &b, int k, double x, double y, doubl
     RotBlit &rb = *rbp;
     const bool integral = x == pg_dfloor(x) && y == pg_dfloor(y) && w == pg_dfloor(w) && h == pg_dfloor(h);
     if (!integral) {
-        if (!(x == 46.66666793823242 && y == 1.3333333730697632 && w == 16.0 && h == 16.0 && pen && (argb_premultiplied >> 24) == 255u))
+        // {x, y, w} of the three non-integer discs of the 64x64 contract, then first row, row count
+        const double rects[3][3] = {{46.66666793823242, 1.3333333730697632, 16.0},            // easy, agent-centred
+                                    {53.60000228881836, 0.800000011920929, 9.600000381469727},   // easy, whole world (center_agent = false)
+                                    {60.400001525878906, 0.4000000059604645, 3.200000047683716}};  // hard, whole world
+        const uint8_t first_row[3] = {1, 0, 0}, n_rows[3] = {17, 11, 4}, row0[3] = {0, 17, 28};
+        const uint8_t rows[32][2] = {{52, 58}, {50, 59}, {49, 60}, {48, 61}, {48, 62}, {47, 63}, {47, 63}, {46, 63}, {46, 63}, {46, 63}, {47, 63},
+                                     {47, 63}, {47, 62}, {48, 61}, {49, 60}, {51, 59}, {53, 57},
+                                     {58, 59}, {56, 61}, {55, 62}, {54, 63}, {53, 63}, {53, 64}, {53, 64}, {54, 64}, {54, 63}, {55, 62}, {57, 61},
+                                     {61, 63}, {60, 64}, {60, 64}, {61, 63}};
+        int which = -1;
+        for (int i = 0; i < 3; i++)
+            if (x == rects[i][0] && y == rects[i][1] && w == rects[i][2] && h == rects[i][2])
+                which = i;
+        if (which < 0 || !pen || (argb_premultiplied >> 24) != 255u)
             return false;
-        const uint8_t rows[17][2] = {{52, 58}, {50, 59}, {49, 60}, {48, 61}, {48, 62}, {47, 63}, {47, 63}, {46, 63}, {46, 63},
-                                     {46, 63}, {47, 63}, {47, 63}, {47, 62}, {48, 61}, {49, 60}, {51, 59}, {53, 57}};
-        for (int i = 0; i < 17; i++) rot_span(rb, rows[i][0], rows[i][1] - rows[i][0], 1 + i);
+        for (int i = 0; i < n_rows[which]; i++) {
+            const uint8_t *r = rows[row0[which] + i];
+            rot_span(rb, r[0], r[1] - r[0], first_row[which] + i);
+        }
         span_blit_finish(b, rb);
         return true;
     }

@@ -547,8 +547,7 @@ libenv_env *libenv_make(int num_envs, const struct libenv_options options) {
         if (!g)
             pg_fatal("unknown or not yet supported env_name '%s'\n", name.c_str());
         // Five games honour center_agent=false by drawing their whole (up to 64x64-cell) world
-        // (basic-abstract-game.cpp:819-838); four of them have a render path sized for that view. jumper's
-        // would also need Qt's generic (non-integer-rect) ellipse for its compass.
+        // (basic-abstract-game.cpp:819-838) through the render path sized for that view.
         int view = 0;
         if (!center_agent && (name == "coinrun" || name == "climber" || name == "caveflyer" || name == "jumper" || name == "ninja")) {
             if (g->step[1] == nullptr)

@@ -159,7 +159,8 @@ def test_restrict_themes_all_games(ref_lib, hostsim_lib, name):
 
 
 @pytest.mark.parametrize("name,mode", [("coinrun", "hard"), ("coinrun", "easy"), ("ninja", "hard"), ("climber", "hard"),
-                                       ("caveflyer", "hard"), ("caveflyer", "memory")])
+                                       ("caveflyer", "hard"), ("caveflyer", "memory"), ("jumper", "easy"), ("jumper", "hard"),
+                                       ("jumper", "memory")])
 def test_whole_world_view_of_scrolling_games(ref_lib, hostsim_lib, name, mode):
     """center_agent=False for the games that otherwise scroll (basic-abstract-game.cpp:819-838): the whole
     world — up to 64 x 64 cells of about one pixel — through the full-view instantiation of the setup /

@@ -382,7 +382,8 @@ def test_consumer_epilogue_matches_torch_ops(product_lib, name, frames, dtype_na
     env.close()
 
 
-@pytest.mark.parametrize("name,mode", [("coinrun", "hard"), ("ninja", "hard"), ("climber", "hard"), ("caveflyer", "hard"), ("caveflyer", "memory")])
+@pytest.mark.parametrize("name,mode", [("coinrun", "hard"), ("ninja", "hard"), ("climber", "hard"), ("caveflyer", "hard"), ("caveflyer", "memory"),
+                                       ("jumper", "easy"), ("jumper", "hard"), ("jumper", "memory")])
 def test_whole_world_view_of_scrolling_games(ref_lib, product_lib, name, mode):
     """center_agent=False (basic-abstract-game.cpp:819-838) for the scrolling games: the full-view kernels."""
     ref, dut = make_pair(product_lib, 8, name, distribution_mode=mode, num_levels=200, start_level=0, rand_seed=0,
