@@ -92,6 +92,26 @@ def _nvcc():
     return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
+VALIDATED_NVCC = ("release 12.9",)
+
+
+def check_toolchain():
+    """The logic kernel runs each env's scalar step on all 32 lanes of a warp in lockstep (pg_engine.cuh); the
+    bit-exact GPU suite is what proves a given compiler keeps the lanes converged between the __syncwarp points.
+    A compiler outside the validated list still builds, but says so: re-run `pytest -m gpu` before trusting it."""
+    import sys
+
+    try:
+        txt = subprocess.run([_nvcc(), "--version"], capture_output=True, text=True, check=True).stdout
+    except (OSError, subprocess.CalledProcessError):
+        return None
+    if not any(v in txt for v in VALIDATED_NVCC):
+        print(f"procgen_b200: nvcc is not one of the validated releases {VALIDATED_NVCC}; run the GPU parity suite "
+              "(pytest -m gpu) before using this build", file=sys.stderr)
+        return False
+    return True
+
+
 def build_variant(name, extra_flags):
     """A tuning variant of the product library (same sources, extra -D flags) next to it; selected at
     run time with PROCGEN_B200_LIB. Used by tools/ for A/B kernel experiments only."""
@@ -105,6 +125,7 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     extra = os.environ.get("PG_NVCC_EXTRA", "").split()
+    check_toolchain()
     objs = _compile_all(os.path.join(CSRC, "_obj", "product"), [_nvcc(), *NVCC_FLAGS, *extra], "product", force, verbose)
     tmp = LIB_PATH + ".building"
     subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", tmp, "-lz", "-ldl"])

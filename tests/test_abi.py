@@ -54,3 +54,12 @@ def test_package_refuses_non_cuda_build(hostsim_lib):
     finally:
         L.LIB_PATH = saved
         L._lib = None
+
+
+def test_compiler_is_a_validated_release():
+    """The warp-lockstep execution of the per-env scalar logic (pg_engine.cuh) is proven per compiler by the
+    bit-exact GPU suite; build.py lists the nvcc releases that suite ran against and warns for any other."""
+    from procgen_b200 import build
+
+    ok = build.check_toolchain()
+    assert ok is not False, "nvcc release not in build.VALIDATED_NVCC: run pytest -m gpu, then add it"

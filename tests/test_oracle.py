@@ -109,6 +109,35 @@ def test_raster_restatement_matches_real_qt6(ref_lib, asset_pack):
         b.close()
 
 
+def test_whole_world_view_restatement_matches_real_qt6(ref_lib, asset_pack):
+    """center_agent=False (basic-abstract-game.cpp:819-838): cells of 1 to 3.2 px, and jumper's compass disc on
+    the two further non-integer rects whose rows were captured from Qt 6.6.3 — restatement == real Qt 6."""
+    from oracle import qt6_support
+    from oracle.ref_env import REF_LIB_QT6
+
+    if not qt6_support.available() or not os.path.exists(REF_LIB_QT6):
+        pytest.skip("Qt 6 backed oracle not available")
+    for name, mode in [("jumper", "easy"), ("jumper", "hard"), ("jumper", "memory"), ("coinrun", "hard"), ("caveflyer", "hard"),
+                       ("climber", "hard"), ("ninja", "easy")]:
+        n, steps = 4, 120
+        a = RefVecEnv(n, name, distribution_mode=mode, num_levels=0, rand_seed=5, center_agent=False)
+        b = RefVecEnv(n, name, distribution_mode=mode, num_levels=0, rand_seed=5, center_agent=False, lib_path=REF_LIB_QT6)
+        acts = mt19937_actions(2, n, steps)
+        bad = tot = 0
+        for t in range(steps):
+            a.act(acts[t])
+            b.act(acts[t])
+            _, oa, _ = a.observe()
+            _, ob, _ = b.observe()
+            d = (oa["rgb"] != ob["rgb"]).any(-1)
+            bad += int(d.sum())
+            tot += d.size
+        a.close()
+        b.close()
+        # caveflyer's ship rotates: the coverage budget of test_rotated_raster_restatement_close_to_real_qt6 applies
+        assert bad <= (1e-5 * tot if name == "caveflyer" else 0), f"{name} {mode}: {bad} of {tot} pixels differ from Qt 6.6.3"
+
+
 def test_rotated_raster_restatement_close_to_real_qt6(ref_lib, asset_pack):
     """Rotated sprites (heist): the restatement follows Qt's two transformed-image paths. Texels are
     exact; coverage of small quads differs from Qt 6.6.3 only at exact 45-degree headings (26.6
@@ -171,10 +200,12 @@ def test_ellipse_and_line_restatement_match_real_qt6(ref_lib, asset_pack):
                 for h in (1, 2, 3, 8, 16, w):
                     for col, pw in (((168, 166, 158, 255), 1), ((255, 255, 255, 120), -1), ((252, 186, 3, 255), 0)):
                         assert np.array_equal(ell(mine, x, y, w, h, col, pw), ell(qt, x, y, w, h, col, pw)), (x, y, w, h, col, pw)
-    # jumper's two compass discs (jumper.cpp:138-141): easy mode's sits on a non-integer rect
+    # jumper's four compass discs (jumper.cpp:138-141): all but hard mode's centred one sit on non-integer rects
     unit = np.float32(64) / np.float32(12)
     easy = (float(np.float32(8.75) * unit), float(np.float32(.25) * unit), float(np.float32(3) * unit))
-    for rect in ((easy[0], easy[1], easy[2], easy[2]), (55.0, 1.0, 8.0, 8.0)):
+    world_easy = (53.60000228881836, 0.800000011920929, 9.600000381469727)   # center_agent=False, tests/tools/qt6_compass_mask.py
+    world_hard = (60.400001525878906, 0.4000000059604645, 3.200000047683716)
+    for rect in ((easy[0], easy[1], easy[2], easy[2]), (55.0, 1.0, 8.0, 8.0), world_easy + world_easy[2:], world_hard + world_hard[2:]):
         assert np.array_equal(ell(mine, *rect, (168, 166, 158, 255), 1), ell(qt, *rect, (168, 166, 158, 255), 1)), rect
     # every needle the compass can draw and more: all integer offsets within 9 px of in-bounds centres
     for cx, cy in ((54, 9), (59, 5), (20, 40), (10, 10)):
